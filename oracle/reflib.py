@@ -1,0 +1,141 @@
+"""TEST INFRASTRUCTURE — ctypes bindings for oracle/_ref/libhadi_ref{,_omp}.so (the reference's own
+sources compiled against oracle/kokkos_shim, see oracle/ref_driver.cpp) and for
+oracle/libhadi_oracle.so (the plain-C restatement, oracle/hadi_oracle.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  Nothing in the product package imports it.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(_ip)
+
+
+def ref_path(omp=False):
+    return os.path.join(_HERE, "_ref", "libhadi_ref_omp.so" if omp else "libhadi_ref.so")
+
+
+def have_ref(omp=False):
+    return os.path.exists(ref_path(omp))
+
+
+class RefLib:
+    """The real reference (unmodified sources) behind a C ABI."""
+
+    def __init__(self, omp=False):
+        self.lib = C.CDLL(ref_path(omp))
+        L = self.lib
+        L.hadi_ref_grid.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int,
+                                    C.c_double, C.c_double, C.c_double, _dp, _dp, _dp, _dp]
+        L.hadi_ref_solve_batch.argtypes = (
+            [C.c_int, _dp, _dp, _ip, _dp] + [C.c_double] * 8 + [C.c_int, C.c_int, C.c_double, C.c_int,
+                                                               C.c_int, C.c_int, _dp, _dp, _dp, C.c_int,
+                                                               C.c_int, C.c_double, C.c_double, _dp, _dp,
+                                                               _dp, _dp])
+        L.hadi_ref_lm_update.argtypes = [C.c_int, _dp, _dp, C.c_double, _dp]
+        L.hadi_ref_solve5.argtypes = [_dp, _dp, _dp]
+        L.hadi_ref_bs_call.argtypes = [C.c_double] * 5
+        L.hadi_ref_bs_call.restype = C.c_double
+        L.hadi_ref_host_scheme.argtypes = ([C.c_int] + [C.c_double] * 10 + [C.c_int, C.c_int, C.c_int,
+                                                                            C.c_double, _dp, _dp])
+        L.hadi_ref_dump_operators.argtypes = ([C.c_double, C.c_int] + [C.c_double] * 9 +
+                                              [C.c_int, C.c_int, C.c_double] + [_dp] * 8)
+        L.hadi_ref_run_shipped.argtypes = [C.c_int]
+
+    def grid(self, m1, m2, K, S0, V0, S=None, c=None, V=5.0, d=5.0 / 500):
+        S = 8 * K if S is None else S
+        c = K / 5 if c is None else c
+        s, ds = np.zeros(m1 + 1), np.zeros(m1)
+        v, dv = np.zeros(m2 + 1), np.zeros(m2)
+        self.lib.hadi_ref_grid(m1, S, S0, K, c, m2, V, V0, d, _d(s), _d(ds), _d(v), _d(dv))
+        return s, ds, v, dv
+
+    def solve_batch(self, strikes, N, dt, *, S0, V0, r_d, r_f, rho, sigma, kappa, eta, m1, m2, theta,
+                    style=0, payoff_put=0, divs=None, multi=0, jac=0, eps=1e-6, maturities=None,
+                    want_U=False, want_lambda=False, V0_grid=None):
+        strikes = np.ascontiguousarray(strikes, dtype=np.float64)
+        n = strikes.size
+        Ns = np.ascontiguousarray(np.broadcast_to(np.asarray(N, dtype=np.int32), (n,)))
+        dts = np.ascontiguousarray(np.broadcast_to(np.asarray(dt, dtype=np.float64), (n,)))
+        mats = None if maturities is None else np.ascontiguousarray(
+            np.broadcast_to(np.asarray(maturities, dtype=np.float64), (n,)))
+        P = (m1 + 1) * (m2 + 1)
+        prices = np.zeros(n)
+        J = np.zeros((n, 5)) if jac else None
+        U = np.zeros((n, P)) if want_U else None
+        lam = np.zeros((n, P)) if want_lambda else None
+        if divs is not None and len(divs[0]) > 0:
+            dd, da, dp = (np.ascontiguousarray(x, dtype=np.float64) for x in divs)
+            nd = dd.size
+        else:
+            dd = da = dp = None
+            nd = 0
+        rc = self.lib.hadi_ref_solve_batch(
+            n, _d(strikes), _d(mats), _i(Ns), _d(dts), S0, V0, r_d, r_f, rho, sigma, kappa, eta, m1, m2,
+            theta, style, payoff_put, nd, _d(dd), _d(da), _d(dp), multi, jac, eps,
+            V0 if V0_grid is None else V0_grid, _d(prices), _d(J), _d(U), _d(lam))
+        if rc != 0:
+            raise RuntimeError("hadi_ref_solve_batch rc=%d" % rc)
+        out = {"prices": prices}
+        if jac:
+            out["J"] = J
+        if want_U:
+            out["U"] = U
+        if want_lambda:
+            out["lambda"] = lam
+        return out
+
+    def lm_update(self, J, r, lam):
+        J = np.ascontiguousarray(J, dtype=np.float64)
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        delta = np.zeros(5)
+        self.lib.hadi_ref_lm_update(r.size, _d(J), _d(r), lam, _d(delta))
+        return delta
+
+    def solve5(self, A, b):
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.zeros(5)
+        self.lib.hadi_ref_solve5(_d(A), _d(b), _d(x))
+        return x
+
+    def bs_call(self, S, K, r, vol, T):
+        return self.lib.hadi_ref_bs_call(S, K, r, vol, T)
+
+    def host_scheme(self, scheme, *, K, S0, V0, T, r_d, r_f, rho, sigma, kappa, eta, m1, m2, N, theta,
+                    want_U=False):
+        price = C.c_double(0.0)
+        U = np.zeros((m1 + 1) * (m2 + 1)) if want_U else None
+        rc = self.lib.hadi_ref_host_scheme(scheme, K, S0, V0, T, r_d, r_f, rho, sigma, kappa, eta, m1,
+                                           m2, N, theta, C.byref(price), _d(U))
+        if rc != 0:
+            raise RuntimeError("hadi_ref_host_scheme rc=%d" % rc)
+        return (price.value, U) if want_U else price.value
+
+    def dump_operators(self, *, K, N, dt, S0, V0, r_d, r_f, rho, sigma, kappa, eta, m1, m2, theta):
+        P = (m1 + 1) * (m2 + 1)
+        a1l, a1m, a1u = np.zeros(P), np.zeros(P), np.zeros(P)
+        a2 = np.zeros(5 * (m2 + 1))
+        b, b1, b2 = np.zeros(P), np.zeros(P), np.zeros(P)
+        a0 = np.zeros((m2 - 1) * (m1 - 1) * 9)
+        self.lib.hadi_ref_dump_operators(K, N, dt, S0, V0, r_d, r_f, rho, sigma, kappa, eta, m1, m2,
+                                         theta, _d(a1l), _d(a1m), _d(a1u), _d(a2), _d(b), _d(b1), _d(b2),
+                                         _d(a0))
+        return dict(a1_lower=a1l.reshape(m2 + 1, m1 + 1), a1_main=a1m.reshape(m2 + 1, m1 + 1),
+                    a1_upper=a1u.reshape(m2 + 1, m1 + 1), a2=a2.reshape(5, m2 + 1), b=b, b1=b1, b2=b2,
+                    a0=a0.reshape(m2 - 1, (m1 - 1) * 9))
+
+    def run_shipped(self, which):
+        return self.lib.hadi_ref_run_shipped(which)
