@@ -1,0 +1,188 @@
+/* hadi.h — C ABI of the B200-native batched Heston ADI pricing / calibration engine.
+ *
+ * Drop-in boundary for the solver and calibration entry points of
+ * BCW-dot/PDE-based-Heston-Solver-GPU-accelerated (citations relative to that repository):
+ *
+ *   reference entry point (host function that launches one Kokkos kernel)       replaced by
+ *   ---------------------------------------------------------------------------------------------
+ *   compute_base_prices{,_american,_dividends,_american_dividends}              hadi_price_batch
+ *       src/jacobian_computation.hpp:82-104,127-143,168-189,216-237
+ *   compute_base_prices_multi_maturity{,_american_dividends}                    hadi_price_batch
+ *       src/heston_calibration.cpp:2339,3140                                    (per-point N, dt)
+ *   compute_jacobian{,_american,_dividends,_american_dividends}                 hadi_jacobian_batch
+ *       src/jacobian_computation.hpp:43-80,106-125,145-166,191-214
+ *   compute_jacobian_multi_maturity{,_american_dividends}                       hadi_jacobian_batch
+ *       src/heston_calibration.cpp:2174,2936
+ *   compute_parameter_update_on_device  src/jacobian_computation.hpp:36-41      hadi_lm_update
+ *   solve_5x5_device                    src/jacobian_computation.hpp:28-33      hadi_solve5
+ *   LM loops of test_calibration_*      src/heston_calibration.cpp:204-417,     hadi_calibrate
+ *                                       2692-2831, 3568-3716
+ *   CalibrationPoint                    src/heston_calibration.cpp:2165-2171    hadi_point
+ *   parallel_DO_solve                   src/device_solver.hpp:53                hadi_price_batch
+ *
+ * Conventions
+ *   - Plain C types only.  All pointers are HOST pointers unless the name ends in _dev.
+ *   - Grids are built inside the library exactly as every reference caller builds them:
+ *     Grid(m1, 8K, S0, K, K/5, m2, 5.0, V0, 5.0/500)  (src/grid.cpp:16, src/heston_calibration.cpp:2614),
+ *     the variance grid being rebuilt for the current V0 as GridViews::rebuild_variance_views does
+ *     (src/grid_pod.hpp:25).  The payoff U_0 the reference takes as an input array is generated from
+ *     `payoff` (max(s-K,0) or max(K-s,0)); boundary vectors are the reference's call vectors.
+ *   - Jacobian / delta column order: (kappa, eta, sigma, rho, v0)  (src/jacobian_computation.cpp:299-304,332).
+ *   - Every function returns HADI_OK (0) or a negative error code; nothing throws across the ABI.
+ *   - A hadi_ctx is bound to one CUDA device and must be used from one host thread at a time.
+ *   - There is NO CPU fallback: if no CUDA device is usable hadi_create fails with HADI_ERR_CUDA.
+ */
+#ifndef HADI_H
+#define HADI_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HADI_OK 0
+#define HADI_ERR_ARG (-1)        /* bad shape / null pointer / unsupported combination */
+#define HADI_ERR_GRID (-2)       /* S0 is not a node of some option's s-grid (reference: index_s = -1, UB) */
+#define HADI_ERR_CUDA (-3)       /* CUDA runtime error (see hadi_last_error) */
+#define HADI_ERR_SMEM (-4)       /* grid does not fit the shared-memory resident kernel */
+#define HADI_ERR_COMM (-5)       /* multi-GPU exchange failed */
+#define HADI_ERR_NOMEM (-6)
+
+#define HADI_EUROPEAN 0
+#define HADI_AMERICAN 1
+#define HADI_CALL 0
+#define HADI_PUT 1               /* put PAYOFF under the reference's call boundary vectors */
+#define HADI_DOUGLAS 0
+#define HADI_CRAIG_SNEYD 1
+
+typedef struct hadi_ctx hadi_ctx;
+typedef struct hadi_batch hadi_batch;
+
+/* Market + model parameters: the scalar arguments S_0, V_0, r_d, r_f, rho, sigma, kappa, eta of
+ * compute_base_prices / compute_jacobian (src/jacobian_computation.hpp:45-47). */
+typedef struct {
+  double S0, V0, r_d, r_f;
+  double kappa, eta, sigma, rho;
+} hadi_model;
+
+/* One option to price.  Same fields and meaning as the reference's CalibrationPoint
+ * (src/heston_calibration.cpp:2165-2171); results are written at position global_index. */
+typedef struct {
+  double strike;
+  double maturity;
+  int time_steps;   /* N */
+  double delta_t;   /* maturity / N as computed by the caller */
+  int global_index;
+} hadi_point;
+
+/* Numerical set-up shared by a batch: m1, m2, theta of the reference signatures, the variant
+ * (which of the four reference functions), and the dividend schedule (dates in time-to-maturity
+ * units as the reference compares them with t = n*dt: src/device_solver.hpp:432-516). */
+typedef struct {
+  int m1, m2;
+  double theta;
+  int style;        /* HADI_EUROPEAN | HADI_AMERICAN */
+  int payoff;       /* HADI_CALL | HADI_PUT */
+  int scheme;       /* HADI_DOUGLAS (device path of the reference) | HADI_CRAIG_SNEYD */
+  int num_dividends;
+  const double* dividend_dates;
+  const double* dividend_amounts;
+  const double* dividend_percentages;
+} hadi_numerics;
+
+typedef struct {
+  int max_iter;      /* reference: 15 (multi-maturity), 20 (American dividends) */
+  double tol;        /* stop when sum r^2 < tol          (src/heston_calibration.cpp:2544) */
+  double delta_tol;  /* stop when ||delta||_2 < delta_tol (:2545) */
+  double lambda0;    /* 0.01 (:2676) */
+  double eps;        /* finite-difference bump, 1e-6 (:2457) */
+} hadi_lm_options;
+
+typedef struct {
+  double params[5];  /* kappa, eta, sigma, rho, v0 */
+  double final_error;
+  double lambda;
+  double delta_norm;
+  int iterations;
+  int converged;
+  int pde_solves;
+  double gpu_ms;     /* device time of all solver launches (CUDA events) */
+} hadi_lm_result;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int hadi_create(hadi_ctx** out, int device);
+void hadi_destroy(hadi_ctx* ctx);
+const char* hadi_last_error(const hadi_ctx* ctx);
+const char* hadi_version(void);
+/* number of hadi kernels launched by this context so far (bench.py's gpu_launches) */
+long long hadi_kernel_launches(const hadi_ctx* ctx);
+
+/* ---- one-call entry points (host buffers in, host buffers out; synchronous) ------------------- */
+/* prices[n]; U_out[n*(m1+1)*(m2+1)] and lambda_out (same shape) may be NULL. */
+int hadi_price_batch(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
+                     const hadi_point* points, double* prices, double* U_out, double* lambda_out);
+/* J[n*5] row-major, base_prices[n]. */
+int hadi_jacobian_batch(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
+                        const hadi_point* points, double eps, double* J, double* base_prices);
+
+/* ---- prepared batches: descriptors + grids resident in HBM, launch / fetch separately --------- */
+#define HADI_MODE_PRICE 0
+#define HADI_MODE_JACOBIAN 1
+/* Work items are options (PRICE) or option x {base, kappa, eta, sigma, rho, v0} (JACOBIAN), item
+ * index = option*6 + column.  [item_begin, item_end) selects the slice this context solves
+ * (multi-GPU sharding); pass 0, -1 for everything. */
+int hadi_batch_create(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
+                      const hadi_point* points, int mode, double eps, int item_begin, int item_end,
+                      hadi_batch** out);
+int hadi_batch_num_items(const hadi_batch* b);
+/* enqueue the solve on the context's stream (asynchronous) */
+int hadi_batch_launch(hadi_batch* b);
+/* device pointer to the item values (one double per item of the slice, slice order) */
+double* hadi_batch_values_dev(hadi_batch* b);
+/* wait and copy the slice's item values to the host (values[item_end-item_begin]) */
+int hadi_batch_fetch(hadi_batch* b, double* values);
+/* elapsed device time of the last launch in ms (CUDA events on the context's stream) */
+int hadi_batch_elapsed_ms(hadi_batch* b, float* ms);
+void hadi_batch_destroy(hadi_batch* b);
+
+/* Jacobian assembly from the full [n*6] item values: base = v[6k], J[k][c] = (v[6k+1+c]-v[6k])/eps
+ * (src/jacobian_computation.cpp:330,361). */
+int hadi_jacobian_assemble(int n, const double* item_values, double eps, double* J, double* base_prices);
+
+/* Static block partition of item costs over `world` ranks (contiguous, balanced by cost). */
+int hadi_partition(int n_items, const int* costs, int world, int rank, int* begin, int* end);
+/* cost (N*P) of each item of a would-be batch, for hadi_partition; costs[n] or costs[6n] */
+int hadi_item_costs(const hadi_numerics* num, int n, const hadi_point* points, int mode, int* costs);
+
+/* ---- Levenberg-Marquardt ---------------------------------------------------------------------- */
+int hadi_solve5(const double* A, const double* b, double* x);
+int hadi_lm_update(int n, const double* J, const double* residual, double lambda, double* delta);
+
+/* Optional exchange hook for multi-GPU calibration: called with this rank's slice of item values
+ * (host buffer) and must fill `all` with every rank's slice in rank order (an all-gather).
+ * counts/displs are in doubles.  Return 0 on success. */
+typedef int (*hadi_allgather_fn)(void* user, const double* mine, int my_count, double* all,
+                                 const int* counts, const int* displs, int world);
+typedef struct {
+  int rank, world;
+  hadi_allgather_fn allgather;
+  void* user;
+} hadi_comm;
+
+/* Full LM calibration (host loop of src/heston_calibration.cpp:2692-2831 around the batched
+ * solver).  comm may be NULL (single GPU). */
+int hadi_calibrate(hadi_ctx* ctx, const hadi_model* initial, const hadi_numerics* num, int n,
+                   const hadi_point* points, const double* market_prices, const hadi_lm_options* opt,
+                   const hadi_comm* comm, hadi_lm_result* result);
+
+/* ---- host helpers restating small reference utilities ---------------------------------------- */
+/* Grid::Grid (src/grid.cpp:16-96) with the callers' constants; s[m1+1], v[m2+1] */
+int hadi_grid(int m1, int m2, double K, double S0, double V0, double* s, double* v);
+/* BlackScholes::call_price (src/bs.hpp:44-55) */
+double hadi_bs_call(double S, double K, double r, double vol, double T);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HADI_H */

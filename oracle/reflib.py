@@ -139,3 +139,140 @@ class RefLib:
 
     def run_shipped(self, which):
         return self.lib.hadi_ref_run_shipped(which)
+
+
+# --------------------------------------------------------------------------- plain-C restatement
+class _Model(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("S0", "V0", "r_d", "r_f", "kappa", "eta", "sigma", "rho")]
+
+
+class _Numerics(C.Structure):
+    _fields_ = [("m1", C.c_int), ("m2", C.c_int), ("theta", C.c_double), ("style", C.c_int),
+                ("payoff_put", C.c_int), ("scheme", C.c_int), ("nd", C.c_int), ("div_dates", _dp),
+                ("div_amounts", _dp), ("div_pcts", _dp)]
+
+
+class _LmOpts(C.Structure):
+    _fields_ = [("max_iter", C.c_int), ("tol", C.c_double), ("delta_tol", C.c_double),
+                ("lambda0", C.c_double), ("eps", C.c_double)]
+
+
+class _LmResult(C.Structure):
+    _fields_ = [("params", C.c_double * 5), ("final_error", C.c_double), ("lambda_", C.c_double),
+                ("delta_norm", C.c_double), ("iterations", C.c_int), ("converged", C.c_int),
+                ("pde_solves", C.c_int)]
+
+
+def oracle_path():
+    return os.path.join(_HERE, "libhadi_oracle.so")
+
+
+class OracleLib:
+    """oracle/hadi_oracle.c — the CPU restatement ("port")."""
+
+    def __init__(self):
+        self.lib = C.CDLL(oracle_path())
+        L = self.lib
+        L.ho_grid_s.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _dp, _dp]
+        L.ho_grid_v.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, _dp, _dp]
+        L.ho_solve.argtypes = [C.POINTER(_Model), C.POINTER(_Numerics), C.c_double, C.c_int, C.c_double,
+                               C.c_double, _dp, _dp, _dp]
+        L.ho_price_batch.argtypes = [C.POINTER(_Model), C.POINTER(_Numerics), C.c_int, _dp, _ip, _dp, _dp]
+        L.ho_jacobian_batch.argtypes = [C.POINTER(_Model), C.POINTER(_Numerics), C.c_int, _dp, _ip, _dp,
+                                        C.c_double, _dp, _dp]
+        L.ho_solve5.argtypes = [_dp, _dp, _dp]
+        L.ho_lm_update.argtypes = [C.c_int, _dp, _dp, C.c_double, _dp]
+        L.ho_calibrate.argtypes = [C.POINTER(_Model), C.POINTER(_Numerics), C.c_int, _dp, _ip, _dp, _dp,
+                                   C.POINTER(_LmOpts), C.POINTER(_LmResult)]
+        L.ho_bs_call.argtypes = [C.c_double] * 5
+        L.ho_bs_call.restype = C.c_double
+
+    @staticmethod
+    def _mk(S0, V0, r_d, r_f, rho, sigma, kappa, eta, m1, m2, theta, style=0, payoff_put=0, scheme=0,
+            divs=None):
+        mdl = _Model(S0, V0, r_d, r_f, kappa, eta, sigma, rho)
+        keep = []
+        if divs is not None and len(divs[0]) > 0:
+            arrs = [np.ascontiguousarray(x, dtype=np.float64) for x in divs]
+            keep = arrs
+            num = _Numerics(m1, m2, theta, style, payoff_put, scheme, arrs[0].size, _d(arrs[0]),
+                            _d(arrs[1]), _d(arrs[2]))
+        else:
+            num = _Numerics(m1, m2, theta, style, payoff_put, scheme, 0, None, None, None)
+        return mdl, num, keep
+
+    def grid(self, m1, m2, K, S0, V0):
+        s, ds = np.zeros(m1 + 1), np.zeros(m1)
+        v, dv = np.zeros(m2 + 1), np.zeros(m2)
+        self.lib.ho_grid_s(m1, 8 * K, S0, K, K / 5, _d(s), _d(ds))
+        self.lib.ho_grid_v(m2, 5.0, V0, 5.0 / 500, _d(v), _d(dv))
+        return s, ds, v, dv
+
+    def solve(self, K, N, dt, want_U=True, want_lambda=True, **kw):
+        mdl, num, keep = self._mk(**kw)
+        P = (num.m1 + 1) * (num.m2 + 1)
+        price = C.c_double(0.0)
+        U = np.zeros(P) if want_U else None
+        lam = np.zeros(P) if want_lambda else None
+        rc = self.lib.ho_solve(C.byref(mdl), C.byref(num), K, N, dt, mdl.V0, C.byref(price), _d(U),
+                               _d(lam))
+        if rc != 0:
+            raise RuntimeError("ho_solve rc=%d" % rc)
+        return {"price": price.value, "U": U, "lambda": lam}
+
+    @staticmethod
+    def _batch_args(strikes, N, dt):
+        strikes = np.ascontiguousarray(strikes, dtype=np.float64)
+        n = strikes.size
+        Ns = np.ascontiguousarray(np.broadcast_to(np.asarray(N, dtype=np.int32), (n,)))
+        dts = np.ascontiguousarray(np.broadcast_to(np.asarray(dt, dtype=np.float64), (n,)))
+        return strikes, n, Ns, dts
+
+    def price_batch(self, strikes, N, dt, **kw):
+        mdl, num, keep = self._mk(**kw)
+        strikes, n, Ns, dts = self._batch_args(strikes, N, dt)
+        prices = np.zeros(n)
+        rc = self.lib.ho_price_batch(C.byref(mdl), C.byref(num), n, _d(strikes), _i(Ns), _d(dts),
+                                     _d(prices))
+        if rc != 0:
+            raise RuntimeError("ho_price_batch rc=%d" % rc)
+        return prices
+
+    def jacobian_batch(self, strikes, N, dt, eps=1e-6, **kw):
+        mdl, num, keep = self._mk(**kw)
+        strikes, n, Ns, dts = self._batch_args(strikes, N, dt)
+        J, base = np.zeros((n, 5)), np.zeros(n)
+        rc = self.lib.ho_jacobian_batch(C.byref(mdl), C.byref(num), n, _d(strikes), _i(Ns), _d(dts), eps,
+                                        _d(J), _d(base))
+        if rc != 0:
+            raise RuntimeError("ho_jacobian_batch rc=%d" % rc)
+        return J, base
+
+    def lm_update(self, J, r, lam):
+        J = np.ascontiguousarray(J, dtype=np.float64)
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        delta = np.zeros(5)
+        self.lib.ho_lm_update(r.size, _d(J), _d(r), lam, _d(delta))
+        return delta
+
+    def solve5(self, A, b):
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.zeros(5)
+        self.lib.ho_solve5(_d(A), _d(b), _d(x))
+        return x
+
+    def calibrate(self, strikes, N, dt, market, *, max_iter, tol, delta_tol, lambda0=0.01, eps=1e-6, **kw):
+        mdl, num, keep = self._mk(**kw)
+        strikes, n, Ns, dts = self._batch_args(strikes, N, dt)
+        market = np.ascontiguousarray(market, dtype=np.float64)
+        opt = _LmOpts(max_iter, tol, delta_tol, lambda0, eps)
+        res = _LmResult()
+        self.lib.ho_calibrate(C.byref(mdl), C.byref(num), n, _d(strikes), _i(Ns), _d(dts), _d(market),
+                              C.byref(opt), C.byref(res))
+        return dict(params=list(res.params), final_error=res.final_error, lam=res.lambda_,
+                    delta_norm=res.delta_norm, iterations=res.iterations, converged=res.converged,
+                    pde_solves=res.pde_solves)
+
+    def bs_call(self, S, K, r, vol, T):
+        return self.lib.ho_bs_call(S, K, r, vol, T)

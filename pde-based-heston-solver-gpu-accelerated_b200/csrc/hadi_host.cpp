@@ -1,0 +1,772 @@
+// hadi — host layer (C++) behind the C ABI of include/hadi.h.
+//
+// Builds, for a batch of options, everything the reference's callers build before they launch
+// compute_base_prices* / compute_jacobian* (grids, payoffs, per-maturity step tables —
+// src/heston_calibration.cpp:2563-2660), packs it into flat device pools, launches the fused
+// sm_100a kernel (hadi_kernel.cu) and runs the Levenberg-Marquardt driver
+// (src/heston_calibration.cpp:2692-2831, src/jacobian_computation.cpp:20-195).
+//
+// sinh/asinh/exp are evaluated here, on the host, with libm: the oracle (the reference compiled for
+// CPU) uses the same libm, and bit-equal grids are a precondition for bit-equal prices.
+// There is no CPU solver in this file: every PDE solve goes through the CUDA kernel.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/hadi.h"
+#include "hadi_launch.h"
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  bool in_use = false;
+  bool pinned_host = false;
+};
+
+}  // namespace
+
+struct hadi_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int threads = 0, max_smem = 0, sm_count = 0;
+  std::string err;
+  long long launches = 0;
+  std::vector<DevBuf> pool;  // caching allocator: device and pinned-host blocks are reused across batches
+  // s-grids depend only on (m1, K, S0): cache them across calls (an LM run re-prices the same
+  // strikes dozens of times; the reference likewise builds its GridViews once, before the loop).
+  std::map<std::tuple<int, uint64_t, uint64_t>, std::shared_ptr<std::vector<double>>> s_cache;
+  std::map<int, std::shared_ptr<std::vector<double>>> v_base;  // d*sinh(j*d_eta) per m2
+};
+
+struct hadi_batch {
+  hadi_ctx* ctx = nullptr;
+  int n_items = 0;
+  int m1 = 0, m2 = 0;
+  HadiLaunch L{};
+  int grid_ctas = 0;
+  size_t smem = 0;
+  std::vector<int> bufs;  // indices into ctx->pool owned by this batch
+  double* h_values = nullptr;  // pinned
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool launched = false;
+};
+
+namespace {
+
+int fail(hadi_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+int cuda_fail(hadi_ctx* ctx, cudaError_t e, const char* what) {
+  return fail(ctx, HADI_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+uint64_t bits(double x) {
+  uint64_t u;
+  std::memcpy(&u, &x, sizeof u);
+  return u;
+}
+
+int pool_get(hadi_ctx* ctx, size_t bytes, bool pinned_host) {
+  bytes = (bytes + 255) & ~size_t(255);
+  if (bytes == 0) bytes = 256;
+  int best = -1;
+  for (size_t k = 0; k < ctx->pool.size(); ++k) {
+    DevBuf& b = ctx->pool[k];
+    if (!b.in_use && b.pinned_host == pinned_host && b.bytes >= bytes && b.bytes <= 4 * bytes + (1 << 16))
+      if (best < 0 || b.bytes < ctx->pool[best].bytes) best = (int)k;
+  }
+  if (best >= 0) {
+    ctx->pool[best].in_use = true;
+    return best;
+  }
+  DevBuf nb;
+  nb.bytes = bytes;
+  nb.pinned_host = pinned_host;
+  cudaError_t e = pinned_host ? cudaMallocHost(&nb.p, bytes) : cudaMalloc(&nb.p, bytes);
+  if (e != cudaSuccess) {
+    ctx->err = std::string("allocation failed: ") + cudaGetErrorString(e);
+    return -1;
+  }
+  nb.in_use = true;
+  ctx->pool.push_back(nb);
+  return (int)ctx->pool.size() - 1;
+}
+
+// ---- grids (src/grid.cpp:16-96; callers' constants S = 8K, c = K/5, V = 5, d = V/500) ----------
+std::shared_ptr<std::vector<double>> s_grid(hadi_ctx* ctx, int m1, double K, double S0) {
+  auto key = std::make_tuple(m1, bits(K), bits(S0));
+  if (ctx) {
+    auto it = ctx->s_cache.find(key);
+    if (it != ctx->s_cache.end()) return it->second;
+  }
+  const double S = 8 * K, c = K / 5;
+  auto g = std::make_shared<std::vector<double>>(m1 + 1);
+  std::vector<double>& s = *g;
+  const double lo = std::asinh(-K / c);
+  const double dxi = (1.0 / m1) * (std::asinh((S - K) / c) - std::asinh(-K / c));
+  for (int i = 0; i <= m1; ++i) {
+    const double xi = lo + i * dxi;
+    s[i] = K + c * std::sinh(xi);
+  }
+  s.push_back(S0);
+  std::sort(s.begin(), s.end());
+  s.pop_back();  // the reference drops the largest node (quirk Q1)
+  if (ctx) {
+    if (ctx->s_cache.size() > 200000) ctx->s_cache.clear();
+    ctx->s_cache.emplace(key, g);
+  }
+  return g;
+}
+
+// src/grid_pod.hpp:25-73 with V = 5.0, d = 5.0/500 (hard-coded at every reference call site)
+void v_grid(hadi_ctx* ctx, int m2, double V0, double* v) {
+  const double V = 5.0, d = 5.0 / 500;
+  std::shared_ptr<std::vector<double>> base;
+  if (ctx) {
+    auto it = ctx->v_base.find(m2);
+    if (it != ctx->v_base.end()) base = it->second;
+  }
+  if (!base) {
+    base = std::make_shared<std::vector<double>>(m2 + 1);
+    const double deta = (1.0 / m2) * std::asinh(V / d);
+    for (int j = 0; j <= m2; ++j) {
+      const double xi = j * deta;
+      (*base)[j] = d * std::sinh(xi);
+    }
+    if (ctx) ctx->v_base.emplace(m2, base);
+  }
+  std::vector<double> tmp(*base);
+  tmp.push_back(V0);
+  std::sort(tmp.begin(), tmp.end());
+  for (int j = 0; j <= m2; ++j) v[j] = tmp[j];
+}
+
+int find_node(const double* x, int n, double x0) {
+  for (int i = 0; i < n; ++i)
+    if (std::fabs(x[i] - x0) < 1e-10) return i;
+  return -1;
+}
+
+struct Geometry {
+  int m1, m2, ld, n1, n2, pj;
+};
+Geometry geometry(int m1, int m2) {
+  Geometry g;
+  g.m1 = m1;
+  g.m2 = m2;
+  g.ld = (m1 + 1) | 1;  // odd pitch: conflict-free row AND column sweeps for 8-byte words
+  g.n1 = (m1 + 1 + 3) & ~3;
+  g.n2 = (m2 + 1 + 3) & ~3;
+  g.pj = (m2 + 1 + 3) & ~3;
+  return g;
+}
+
+bool valid_numerics(const hadi_numerics* num) {
+  if (!num) return false;
+  if (num->m1 < 4 || num->m2 < 4 || num->m1 > 4096 || num->m2 > 4096) return false;
+  if (num->style != HADI_EUROPEAN && num->style != HADI_AMERICAN) return false;
+  if (num->payoff != HADI_CALL && num->payoff != HADI_PUT) return false;
+  if (num->num_dividends < 0) return false;
+  if (num->num_dividends > 0 &&
+      (!num->dividend_dates || !num->dividend_amounts || !num->dividend_percentages))
+    return false;
+  return true;
+}
+
+int n_columns(int mode) { return mode == HADI_MODE_JACOBIAN ? 6 : 1; }
+
+}  // namespace
+
+extern "C" {
+
+const char* hadi_version(void) { return "hadi 0.1 (sm_100a)"; }
+
+int hadi_create(hadi_ctx** out, int device) {
+  if (!out) return HADI_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) return HADI_ERR_CUDA;
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return HADI_ERR_CUDA;
+  hadi_ctx* ctx = new hadi_ctx();
+  ctx->device = device;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return HADI_ERR_CUDA;
+  }
+  if (hadi_douglas_config(&ctx->threads, &ctx->max_smem, &ctx->sm_count, device) != 0) {
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return HADI_ERR_CUDA;
+  }
+  *out = ctx;
+  return HADI_OK;
+}
+
+void hadi_destroy(hadi_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (DevBuf& b : ctx->pool) {
+    if (b.pinned_host)
+      cudaFreeHost(b.p);
+    else
+      cudaFree(b.p);
+  }
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* hadi_last_error(const hadi_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+long long hadi_kernel_launches(const hadi_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int hadi_grid(int m1, int m2, double K, double S0, double V0, double* s, double* v) {
+  if (m1 < 1 || m2 < 1 || !s || !v) return HADI_ERR_ARG;
+  auto g = s_grid(nullptr, m1, K, S0);
+  std::copy(g->begin(), g->end(), s);
+  v_grid(nullptr, m2, V0, v);
+  return HADI_OK;
+}
+
+double hadi_bs_call(double S, double K, double r, double vol, double T) {
+  // src/bs.hpp:44-55
+  const double sqrt_T = std::sqrt(T);
+  const double log_SK = std::log(S / K);
+  const double vol_sqrt_T = vol * sqrt_T;
+  const double d1 = (log_SK + (r + 0.5 * vol * vol) * T) / vol_sqrt_T;
+  const double d2 = d1 - vol_sqrt_T;
+  return S * std::erfc(-d1 / std::sqrt(2.0)) / 2.0 - K * std::exp(-r * T) * std::erfc(-d2 / std::sqrt(2.0)) / 2.0;
+}
+
+int hadi_item_costs(const hadi_numerics* num, int n, const hadi_point* points, int mode, int* costs) {
+  if (!valid_numerics(num) || n < 0 || (n > 0 && (!points || !costs))) return HADI_ERR_ARG;
+  const int nc = n_columns(mode);
+  const int P = (num->m1 + 1) * (num->m2 + 1);
+  for (int k = 0; k < n; ++k)
+    for (int c = 0; c < nc; ++c) costs[k * nc + c] = points[k].time_steps * P;
+  return HADI_OK;
+}
+
+int hadi_partition(int n_items, const int* costs, int world, int rank, int* begin, int* end) {
+  if (n_items < 0 || world <= 0 || rank < 0 || rank >= world || !begin || !end) return HADI_ERR_ARG;
+  // contiguous blocks; boundary r is the first item whose cost prefix reaches r/world of the total
+  long long total = 0;
+  for (int k = 0; k < n_items; ++k) total += costs ? costs[k] : 1;
+  auto boundary = [&](int r) {
+    if (r <= 0) return 0;
+    if (r >= world) return n_items;
+    const long long target = (total * r + world - 1) / world;
+    long long acc = 0;
+    int k = 0;
+    while (k < n_items && acc < target) {
+      acc += costs ? costs[k] : 1;
+      ++k;
+    }
+    return k;
+  };
+  *begin = boundary(rank);
+  *end = boundary(rank + 1);
+  return HADI_OK;
+}
+
+int hadi_jacobian_assemble(int n, const double* v, double eps, double* J, double* base) {
+  if (n < 0 || !v || !J || !base) return HADI_ERR_ARG;
+  for (int k = 0; k < n; ++k) {
+    const double b = v[6 * k];
+    base[k] = b;
+    for (int c = 0; c < 5; ++c) J[5 * k + c] = (v[6 * k + 1 + c] - b) / eps;
+  }
+  return HADI_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int hadi_batch_create(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
+                      const hadi_point* points, int mode, double eps, int item_begin, int item_end,
+                      hadi_batch** out) {
+  if (!ctx || !out) return HADI_ERR_ARG;
+  *out = nullptr;
+  if (!model || !valid_numerics(num) || n < 0 || (n > 0 && !points)) return fail(ctx, HADI_ERR_ARG, "bad argument");
+  if (mode != HADI_MODE_PRICE && mode != HADI_MODE_JACOBIAN) return fail(ctx, HADI_ERR_ARG, "bad mode");
+  if (num->scheme != HADI_DOUGLAS) return fail(ctx, HADI_ERR_ARG, "scheme not supported by this kernel");
+  const int nc = n_columns(mode);
+  const int total_items = n * nc;
+  if (item_end < 0) item_end = total_items;
+  if (item_begin < 0 || item_begin > item_end || item_end > total_items) return fail(ctx, HADI_ERR_ARG, "bad item range");
+  cudaSetDevice(ctx->device);
+
+  const Geometry g = geometry(num->m1, num->m2);
+  const int m1 = g.m1, m2 = g.m2;
+  const int P = (m1 + 1) * (m2 + 1);
+  const size_t smem = hadi_smem_bytes(m1, m2, g.ld, g.n1, g.n2);
+  if (smem > (size_t)ctx->max_smem) return fail(ctx, HADI_ERR_SMEM, "grid does not fit in shared memory");
+  if (ctx->threads < m1 + 1 || ctx->threads - 1 <= m2) return fail(ctx, HADI_ERR_SMEM, "grid wider than the CTA");
+
+  std::unique_ptr<hadi_batch> b(new hadi_batch());
+  b->ctx = ctx;
+  b->m1 = m1;
+  b->m2 = m2;
+  const int n_items = item_end - item_begin;
+  b->n_items = n_items;
+
+  // ---- host-side descriptors --------------------------------------------------------------
+  std::vector<HadiItem> items(n_items);
+  std::vector<double> s_pool, v_pool, e_pool;
+  std::map<std::pair<uint64_t, uint64_t>, int> s_index;       // (K, S0) -> offset
+  std::map<std::pair<uint64_t, int>, int> e_index;            // (dt, N) -> offset
+  // two v-grids at most: V0 and V0 + eps (src/jacobian_computation.cpp:339)
+  v_pool.resize((size_t)2 * (m2 + 1));
+  v_grid(ctx, m2, model->V0, v_pool.data());
+  const double V0p = model->V0 + eps;
+  v_grid(ctx, m2, V0p, v_pool.data() + (m2 + 1));
+  int idx_v0 = find_node(v_pool.data(), m2 + 1, model->V0);
+  if (idx_v0 < 0) idx_v0 = 0;  // find_v0_index returns 0 when nothing matches (src/grid_pod.hpp:76-87)
+  int idx_v1 = find_node(v_pool.data() + (m2 + 1), m2 + 1, V0p);
+  if (idx_v1 < 0) idx_v1 = 0;
+
+  for (int q = 0; q < n_items; ++q) {
+    const int item = item_begin + q;
+    const int k = item / nc, col = item % nc;
+    const hadi_point& pt = points[k];
+    if (pt.time_steps < 1 || !(pt.delta_t > 0)) return fail(ctx, HADI_ERR_ARG, "bad time stepping");
+    HadiItem it;
+    std::memset(&it, 0, sizeof it);
+    it.kappa = model->kappa;
+    it.eta = model->eta;
+    it.sigma = model->sigma;
+    it.rho = model->rho;
+    // bumps: src/jacobian_computation.cpp:299-304 (param + eps), :339 (grid for V0 + eps)
+    if (col == 1) it.kappa += eps;
+    if (col == 2) it.eta += eps;
+    if (col == 3) it.sigma += eps;
+    if (col == 4) it.rho += eps;
+    it.r_d = model->r_d;
+    it.r_f = model->r_f;
+    it.dt = pt.delta_t;
+    it.theta = num->theta;
+    it.K = pt.strike;
+    it.N = pt.time_steps;
+    it.ef = std::exp(-model->r_f * pt.delta_t * (pt.time_steps - 1));
+    it.style = num->style;
+    it.payoff = num->payoff;
+    it.nd = num->num_dividends;
+    auto skey = std::make_pair(bits(pt.strike), bits(model->S0));
+    auto sit = s_index.find(skey);
+    const double* sg;
+    if (sit == s_index.end()) {
+      auto gs = s_grid(ctx, m1, pt.strike, model->S0);
+      const int off = (int)s_pool.size();
+      s_pool.insert(s_pool.end(), gs->begin(), gs->end());
+      s_index.emplace(skey, off);
+      it.s_off = off;
+    } else {
+      it.s_off = sit->second;
+    }
+    sg = s_pool.data() + it.s_off;
+    it.idx_s = find_node(sg, m1 + 1, model->S0);
+    if (it.idx_s < 0) return fail(ctx, HADI_ERR_GRID, "S0 is not a node of the s-grid");
+    it.v_off = (col == 5) ? (m2 + 1) : 0;
+    it.idx_v = (col == 5) ? idx_v1 : idx_v0;
+    auto ekey = std::make_pair(bits(pt.delta_t), pt.time_steps);
+    auto eit = e_index.find(ekey);
+    if (eit == e_index.end()) {
+      const int off = (int)e_pool.size();
+      for (int nn = 0; nn <= pt.time_steps; ++nn) e_pool.push_back(std::exp(model->r_f * pt.delta_t * nn));
+      e_index.emplace(ekey, off);
+      it.e_off = off;
+    } else {
+      it.e_off = eit->second;
+    }
+    it.out = q;
+    it.cost = pt.time_steps * P;
+    items[q] = it;
+  }
+  // longest items first (the persistent CTAs pull items in order)
+  std::stable_sort(items.begin(), items.end(), [](const HadiItem& a, const HadiItem& c) { return a.cost > c.cost; });
+
+  // ---- device buffers ------------------------------------------------------------------------
+  const int nd = num->num_dividends;
+  const size_t bytes_items = sizeof(HadiItem) * (size_t)std::max(n_items, 1);
+  const size_t bytes_s = sizeof(double) * std::max<size_t>(s_pool.size(), 1);
+  const size_t bytes_v = sizeof(double) * v_pool.size();
+  const size_t bytes_e = sizeof(double) * std::max<size_t>(e_pool.size(), 1);
+  const size_t bytes_d = sizeof(double) * (size_t)std::max(3 * nd, 1);
+  const size_t staging = bytes_items + bytes_s + bytes_v + bytes_e + bytes_d + 5 * 256;
+
+  auto take = [&](size_t bytes, bool pinned) -> void* {
+    const int id = pool_get(ctx, bytes, pinned);
+    if (id < 0) return nullptr;
+    b->bufs.push_back(id);
+    return ctx->pool[id].p;
+  };
+  auto release_all = [&]() {
+    for (int id : b->bufs) ctx->pool[id].in_use = false;
+  };
+  char* h_stage = (char*)take(staging, true);
+  char* d_stage = (char*)take(staging, false);
+  b->h_values = (double*)take(sizeof(double) * (size_t)std::max(n_items, 1), true);
+  double* d_values = (double*)take(sizeof(double) * (size_t)std::max(n_items, 1), false);
+  int* d_counter = (int*)take(256, false);
+
+  int occ = 2;
+  if (2 * (smem + 1024) > (size_t)228 * 1024) occ = 1;
+  b->grid_ctas = std::max(1, std::min(n_items, occ * ctx->sm_count));
+  const size_t stride = (hadi_scratch_doubles(m1, m2, g.ld, g.pj) + 31) & ~size_t(31);
+  double* d_scratch = (double*)take(sizeof(double) * stride * (size_t)b->grid_ctas, false);
+  if (!h_stage || !d_stage || !b->h_values || !d_values || !d_counter || !d_scratch) {
+    release_all();
+    return HADI_ERR_NOMEM;
+  }
+
+  size_t off = 0;
+  auto put = [&](const void* src, size_t bytes) -> size_t {
+    const size_t at = off;
+    if (bytes) std::memcpy(h_stage + at, src, bytes);
+    off = (off + bytes + 255) & ~size_t(255);
+    return at;
+  };
+  const size_t o_items = put(items.data(), sizeof(HadiItem) * (size_t)n_items);
+  const size_t o_s = put(s_pool.data(), sizeof(double) * s_pool.size());
+  const size_t o_v = put(v_pool.data(), bytes_v);
+  const size_t o_e = put(e_pool.data(), sizeof(double) * e_pool.size());
+  std::vector<double> dv((size_t)std::max(3 * nd, 1), 0.0);
+  for (int k = 0; k < nd; ++k) {
+    dv[k] = num->dividend_dates[k];
+    dv[nd + k] = num->dividend_amounts[k];
+    dv[2 * nd + k] = num->dividend_percentages[k];
+  }
+  const size_t o_d = put(dv.data(), sizeof(double) * dv.size());
+  cudaError_t e = cudaMemcpyAsync(d_stage, h_stage, off, cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) {
+    release_all();
+    return cuda_fail(ctx, e, "H2D");
+  }
+
+  HadiLaunch& L = b->L;
+  L.m1 = m1; L.m2 = m2; L.ld = g.ld; L.n1 = g.n1; L.n2 = g.n2; L.pj = g.pj;
+  L.n_items = n_items;
+  L.items = (const HadiItem*)(d_stage + o_items);
+  L.s_pool = (const double*)(d_stage + o_s);
+  L.v_pool = (const double*)(d_stage + o_v);
+  L.e_pool = (const double*)(d_stage + o_e);
+  L.nd = nd;
+  L.div_dates = (const double*)(d_stage + o_d);
+  L.div_amounts = L.div_dates + nd;
+  L.div_pcts = L.div_dates + 2 * nd;
+  L.scratch = d_scratch;
+  L.scratch_stride = stride;
+  L.counter = d_counter;
+  L.out_values = d_values;
+  L.out_U = nullptr;
+  L.out_lam = nullptr;
+  b->smem = smem;
+  if (cudaEventCreate(&b->ev0) != cudaSuccess || cudaEventCreate(&b->ev1) != cudaSuccess) {
+    release_all();
+    return cuda_fail(ctx, cudaGetLastError(), "event");
+  }
+  *out = b.release();
+  return HADI_OK;
+}
+
+int hadi_batch_num_items(const hadi_batch* b) { return b ? b->n_items : 0; }
+double* hadi_batch_values_dev(hadi_batch* b) { return b ? b->L.out_values : nullptr; }
+
+int hadi_batch_launch(hadi_batch* b) {
+  if (!b) return HADI_ERR_ARG;
+  hadi_ctx* ctx = b->ctx;
+  cudaSetDevice(ctx->device);
+  cudaError_t e = cudaMemsetAsync(b->L.counter, 0, sizeof(int), ctx->stream);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "memset");
+  cudaEventRecord(b->ev0, ctx->stream);
+  if (b->n_items > 0) {
+    const int rc = hadi_launch_douglas(b->L, b->grid_ctas, b->smem, ctx->stream);
+    if (rc != 0) return cuda_fail(ctx, (cudaError_t)rc, "kernel launch");
+    ctx->launches++;
+  }
+  cudaEventRecord(b->ev1, ctx->stream);
+  b->launched = true;
+  return HADI_OK;
+}
+
+int hadi_batch_fetch(hadi_batch* b, double* values) {
+  if (!b || (!values && b->n_items > 0)) return HADI_ERR_ARG;
+  hadi_ctx* ctx = b->ctx;
+  cudaSetDevice(ctx->device);
+  cudaError_t e = cudaMemcpyAsync(b->h_values, b->L.out_values, sizeof(double) * (size_t)std::max(b->n_items, 1),
+                                  cudaMemcpyDeviceToHost, ctx->stream);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "D2H");
+  e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "kernel execution");
+  if (b->n_items > 0) std::memcpy(values, b->h_values, sizeof(double) * (size_t)b->n_items);
+  return HADI_OK;
+}
+
+int hadi_batch_elapsed_ms(hadi_batch* b, float* ms) {
+  if (!b || !ms || !b->launched) return HADI_ERR_ARG;
+  cudaSetDevice(b->ctx->device);
+  cudaError_t e = cudaEventSynchronize(b->ev1);
+  if (e != cudaSuccess) return cuda_fail(b->ctx, e, "event sync");
+  e = cudaEventElapsedTime(ms, b->ev0, b->ev1);
+  if (e != cudaSuccess) return cuda_fail(b->ctx, e, "event elapsed");
+  return HADI_OK;
+}
+
+void hadi_batch_destroy(hadi_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->ctx->device);
+  cudaStreamSynchronize(b->ctx->stream);
+  for (int id : b->bufs) b->ctx->pool[id].in_use = false;
+  if (b->ev0) cudaEventDestroy(b->ev0);
+  if (b->ev1) cudaEventDestroy(b->ev1);
+  delete b;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int run_items(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
+                     const hadi_point* points, int mode, double eps, int begin, int end, double* values,
+                     double* U_out, double* lam_out, float* ms) {
+  hadi_batch* b = nullptr;
+  int rc = hadi_batch_create(ctx, model, num, n, points, mode, eps, begin, end, &b);
+  if (rc != HADI_OK) return rc;
+  const size_t P = (size_t)(num->m1 + 1) * (size_t)(num->m2 + 1);
+  int idU = -1, idL = -1;
+  if (U_out) {
+    idU = pool_get(ctx, sizeof(double) * P * (size_t)std::max(b->n_items, 1), false);
+    if (idU < 0) { hadi_batch_destroy(b); return HADI_ERR_NOMEM; }
+    b->bufs.push_back(idU);
+    b->L.out_U = (double*)ctx->pool[idU].p;
+  }
+  if (lam_out) {
+    idL = pool_get(ctx, sizeof(double) * P * (size_t)std::max(b->n_items, 1), false);
+    if (idL < 0) { hadi_batch_destroy(b); return HADI_ERR_NOMEM; }
+    b->bufs.push_back(idL);
+    b->L.out_lam = (double*)ctx->pool[idL].p;
+    cudaMemsetAsync(b->L.out_lam, 0, sizeof(double) * P * (size_t)std::max(b->n_items, 1), ctx->stream);
+  }
+  rc = hadi_batch_launch(b);
+  if (rc == HADI_OK) rc = hadi_batch_fetch(b, values);
+  if (rc == HADI_OK && U_out)
+    if (cudaMemcpy(U_out, b->L.out_U, sizeof(double) * P * (size_t)b->n_items, cudaMemcpyDeviceToHost) != cudaSuccess)
+      rc = cuda_fail(ctx, cudaGetLastError(), "D2H U");
+  if (rc == HADI_OK && lam_out)
+    if (cudaMemcpy(lam_out, b->L.out_lam, sizeof(double) * P * (size_t)b->n_items, cudaMemcpyDeviceToHost) != cudaSuccess)
+      rc = cuda_fail(ctx, cudaGetLastError(), "D2H lambda");
+  if (rc == HADI_OK && ms) hadi_batch_elapsed_ms(b, ms);
+  hadi_batch_destroy(b);
+  return rc;
+}
+
+int hadi_price_batch(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
+                     const hadi_point* points, double* prices, double* U_out, double* lambda_out) {
+  if (!ctx || !prices) return HADI_ERR_ARG;
+  std::vector<double> vals((size_t)std::max(n, 1));
+  const int rc = run_items(ctx, model, num, n, points, HADI_MODE_PRICE, 0.0, 0, -1, vals.data(), U_out, lambda_out, nullptr);
+  if (rc != HADI_OK) return rc;
+  // results land at CalibrationPoint::global_index, as in the reference's multi-maturity drivers
+  for (int k = 0; k < n; ++k) {
+    const int gi = points[k].global_index;
+    if (gi < 0 || gi >= n) return fail(ctx, HADI_ERR_ARG, "global_index out of range");
+    prices[gi] = vals[k];
+  }
+  return HADI_OK;
+}
+
+int hadi_jacobian_batch(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
+                        const hadi_point* points, double eps, double* J, double* base_prices) {
+  if (!ctx || !J || !base_prices) return HADI_ERR_ARG;
+  std::vector<double> vals((size_t)std::max(6 * n, 1)), Jt((size_t)std::max(5 * n, 1)), bt((size_t)std::max(n, 1));
+  int rc = run_items(ctx, model, num, n, points, HADI_MODE_JACOBIAN, eps, 0, -1, vals.data(), nullptr, nullptr, nullptr);
+  if (rc != HADI_OK) return rc;
+  hadi_jacobian_assemble(n, vals.data(), eps, Jt.data(), bt.data());
+  for (int k = 0; k < n; ++k) {
+    const int gi = points[k].global_index;
+    if (gi < 0 || gi >= n) return fail(ctx, HADI_ERR_ARG, "global_index out of range");
+    base_prices[gi] = bt[k];
+    for (int c = 0; c < 5; ++c) J[5 * gi + c] = Jt[5 * k + c];
+  }
+  return HADI_OK;
+}
+
+// ---- Levenberg-Marquardt ----------------------------------------------------------------------
+// src/jacobian_computation.cpp:20-104
+int hadi_solve5(const double* Ain, const double* bin, double* x) {
+  if (!Ain || !bin || !x) return HADI_ERR_ARG;
+  const int N = 5;
+  double A[25], b[5];
+  for (int i = 0; i < N; ++i) {
+    b[i] = bin[i];
+    for (int j = 0; j < N; ++j) A[i * N + j] = Ain[i * N + j];
+  }
+  for (int k = 0; k < N; ++k) {
+    double maxA = std::fabs(A[k * N + k]);
+    int piv = k;
+    for (int p = k + 1; p < N; ++p) {
+      const double val = std::fabs(A[p * N + k]);
+      if (val > maxA) {
+        maxA = val;
+        piv = p;
+      }
+    }
+    if (piv != k) {
+      for (int c = 0; c < N; ++c) std::swap(A[k * N + c], A[piv * N + c]);
+      std::swap(b[k], b[piv]);
+    }
+    const double pivot = A[k * N + k];
+    for (int c = k + 1; c < N; ++c) A[k * N + c] /= pivot;
+    b[k] /= pivot;
+    A[k * N + k] = 1.0;
+    for (int i = k + 1; i < N; ++i) {
+      const double f = A[i * N + k];
+      for (int c = k + 1; c < N; ++c) A[i * N + c] -= f * A[k * N + c];
+      b[i] -= f * b[k];
+      A[i * N + k] = 0.0;
+    }
+  }
+  for (int k = N - 1; k >= 0; --k) {
+    double val = b[k];
+    for (int c = k + 1; c < N; ++c) val -= A[k * N + c] * b[c];
+    b[k] = val;
+  }
+  for (int i = 0; i < N; ++i) x[i] = b[i];
+  return HADI_OK;
+}
+
+// src/jacobian_computation.cpp:107-195.  The 5x5 normal equations are formed on the host in the
+// oracle's (ascending-k) summation order: 30 dot products of length n are not GPU work.
+int hadi_lm_update(int n, const double* J, const double* r, double lambda, double* delta) {
+  if (n < 0 || !J || !r || !delta) return HADI_ERR_ARG;
+  double A[25], g[5];
+  for (int i = 0; i < 5; ++i)
+    for (int j = 0; j < 5; ++j) {
+      double acc = 0.0;
+      for (int k = 0; k < n; ++k) acc += J[k * 5 + i] * J[k * 5 + j];
+      A[i * 5 + j] = acc;
+    }
+  for (int i = 0; i < 5; ++i) A[i * 5 + i] *= (1.0 + lambda);
+  for (int i = 0; i < 5; ++i) {
+    double acc = 0.0;
+    for (int k = 0; k < n; ++k) acc += J[k * 5 + i] * r[k];
+    g[i] = acc;
+  }
+  return hadi_solve5(A, g, delta);
+}
+
+// Solve the items of [0, n*nc) across the ranks of `comm` and return every item value on every rank.
+static int solve_all(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
+                     const hadi_point* points, int mode, double eps, const hadi_comm* comm, double* all,
+                     float* ms) {
+  const int nc = n_columns(mode);
+  const int total = n * nc;
+  if (!comm || comm->world <= 1)
+    return run_items(ctx, model, num, n, points, mode, eps, 0, total, all, nullptr, nullptr, ms);
+  std::vector<int> costs((size_t)std::max(total, 1)), counts(comm->world), displs(comm->world);
+  hadi_item_costs(num, n, points, mode, costs.data());
+  for (int r = 0; r < comm->world; ++r) {
+    int b, e;
+    hadi_partition(total, costs.data(), comm->world, r, &b, &e);
+    displs[r] = b;
+    counts[r] = e - b;
+  }
+  std::vector<double> mine((size_t)std::max(counts[comm->rank], 1));
+  int rc = run_items(ctx, model, num, n, points, mode, eps, displs[comm->rank], displs[comm->rank] + counts[comm->rank],
+                     mine.data(), nullptr, nullptr, ms);
+  if (rc != HADI_OK) return rc;
+  if (!comm->allgather) return fail(ctx, HADI_ERR_COMM, "no allgather hook");
+  if (comm->allgather(comm->user, mine.data(), counts[comm->rank], all, counts.data(), displs.data(), comm->world) != 0)
+    return fail(ctx, HADI_ERR_COMM, "allgather failed");
+  return HADI_OK;
+}
+
+// src/heston_calibration.cpp:2692-2831 (multi-maturity; the single-maturity twin at :204-417 is the
+// same loop with one (N, dt)).
+int hadi_calibrate(hadi_ctx* ctx, const hadi_model* initial, const hadi_numerics* num, int n,
+                   const hadi_point* points, const double* market, const hadi_lm_options* opt,
+                   const hadi_comm* comm, hadi_lm_result* res) {
+  if (!ctx || !initial || !points || !market || !opt || !res || n <= 0) return HADI_ERR_ARG;
+  for (int k = 0; k < n; ++k)
+    if (points[k].global_index < 0 || points[k].global_index >= n) return fail(ctx, HADI_ERR_ARG, "global_index out of range");
+  hadi_model cur = *initial;
+  double lambda = opt->lambda0;
+  std::vector<double> vals((size_t)6 * n), J((size_t)5 * n), Jt((size_t)5 * n), base(n), bt(n), r(n), newp(n), nv(n);
+  bool converged = false;
+  int iters = 0, solves = 0;
+  double final_error = 100.0, delta_norm = 0.0, gpu_ms = 0.0;
+  for (int iter = 0; iter < opt->max_iter && !converged; ++iter) {
+    float ms = 0.f;
+    int rc = solve_all(ctx, &cur, num, n, points, HADI_MODE_JACOBIAN, opt->eps, comm, vals.data(), &ms);
+    if (rc != HADI_OK) return rc;
+    gpu_ms += ms;
+    solves += 6 * n;
+    hadi_jacobian_assemble(n, vals.data(), opt->eps, Jt.data(), bt.data());
+    for (int k = 0; k < n; ++k) {
+      const int gi = points[k].global_index;
+      base[gi] = bt[k];
+      for (int c = 0; c < 5; ++c) J[5 * gi + c] = Jt[5 * k + c];
+    }
+    for (int i = 0; i < n; ++i) r[i] = market[i] - base[i];
+    double delta[5];
+    hadi_lm_update(n, J.data(), r.data(), lambda, delta);
+    hadi_model nw = cur;
+    nw.kappa = std::max(1e-3, cur.kappa + delta[0]);
+    nw.eta = std::max(1e-2, cur.eta + delta[1]);
+    nw.sigma = std::max(1e-2, cur.sigma + delta[2]);
+    nw.rho = std::min(1.0, std::max(-1.0, cur.rho + delta[3]));
+    nw.V0 = std::max(1e-2, cur.V0 + delta[4]);
+    delta_norm = 0.0;
+    for (int i = 0; i < 5; ++i) delta_norm += delta[i] * delta[i];
+    delta_norm = std::sqrt(delta_norm);
+    double cur_err = 0;
+    for (int i = 0; i < n; ++i) cur_err += r[i] * r[i];
+    if (delta_norm < opt->delta_tol || cur_err < opt->tol) {
+      converged = true;
+      cur = nw;  // the candidate is accepted without being evaluated (:2763-2780)
+      final_error = cur_err;
+      iters = iter + 1;
+      break;
+    }
+    rc = solve_all(ctx, &nw, num, n, points, HADI_MODE_PRICE, 0.0, comm, nv.data(), &ms);
+    if (rc != HADI_OK) return rc;
+    gpu_ms += ms;
+    solves += n;
+    for (int k = 0; k < n; ++k) newp[points[k].global_index] = nv[k];
+    double new_err = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const double rr = market[i] - newp[i];
+      new_err += rr * rr;
+    }
+    if (new_err < cur_err) {
+      cur = nw;
+      lambda = std::max(lambda / 10.0, 1e-7);
+    } else {
+      lambda = std::min(lambda * 10.0, 1e7);
+    }
+    final_error = std::min(new_err, cur_err);
+    iters = iter + 1;
+  }
+  res->params[0] = cur.kappa;
+  res->params[1] = cur.eta;
+  res->params[2] = cur.sigma;
+  res->params[3] = cur.rho;
+  res->params[4] = cur.V0;
+  res->final_error = final_error;
+  res->lambda = lambda;
+  res->delta_norm = delta_norm;
+  res->iterations = iters;
+  res->converged = converged ? 1 : 0;
+  res->pde_solves = solves;
+  res->gpu_ms = gpu_ms;
+  return HADI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,320 @@
+"""ctypes binding of libhadi.so (the C ABI declared in include/hadi.h).
+
+This module is plumbing for tests/ and bench.py: it loads the in-tree shared library, mirrors the
+C structs and turns error codes into exceptions.  All numerical work happens in the CUDA kernel
+behind the C ABI; there is no Python or CPU fallback — if the library (or a CUDA device) is missing
+the calls fail loudly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhadi.so")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+OK, ERR_ARG, ERR_GRID, ERR_CUDA, ERR_SMEM, ERR_COMM, ERR_NOMEM = 0, -1, -2, -3, -4, -5, -6
+EUROPEAN, AMERICAN = 0, 1
+CALL, PUT = 0, 1
+DOUGLAS, CRAIG_SNEYD = 0, 1
+MODE_PRICE, MODE_JACOBIAN = 0, 1
+
+# every symbol include/hadi.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "hadi_create", "hadi_destroy", "hadi_last_error", "hadi_version", "hadi_kernel_launches",
+    "hadi_price_batch", "hadi_jacobian_batch", "hadi_batch_create", "hadi_batch_num_items",
+    "hadi_batch_launch", "hadi_batch_values_dev", "hadi_batch_fetch", "hadi_batch_elapsed_ms",
+    "hadi_batch_destroy", "hadi_jacobian_assemble", "hadi_partition", "hadi_item_costs", "hadi_solve5",
+    "hadi_lm_update", "hadi_calibrate", "hadi_grid", "hadi_bs_call",
+]
+
+
+class Model(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("S0", "V0", "r_d", "r_f", "kappa", "eta", "sigma", "rho")]
+
+
+class Point(C.Structure):
+    _fields_ = [("strike", C.c_double), ("maturity", C.c_double), ("time_steps", C.c_int),
+                ("delta_t", C.c_double), ("global_index", C.c_int)]
+
+
+class Numerics(C.Structure):
+    _fields_ = [("m1", C.c_int), ("m2", C.c_int), ("theta", C.c_double), ("style", C.c_int),
+                ("payoff", C.c_int), ("scheme", C.c_int), ("num_dividends", C.c_int),
+                ("dividend_dates", _dp), ("dividend_amounts", _dp), ("dividend_percentages", _dp)]
+
+
+class LmOptions(C.Structure):
+    _fields_ = [("max_iter", C.c_int), ("tol", C.c_double), ("delta_tol", C.c_double),
+                ("lambda0", C.c_double), ("eps", C.c_double)]
+
+
+class LmResult(C.Structure):
+    _fields_ = [("params", C.c_double * 5), ("final_error", C.c_double), ("lambda_", C.c_double),
+                ("delta_norm", C.c_double), ("iterations", C.c_int), ("converged", C.c_int),
+                ("pde_solves", C.c_int), ("gpu_ms", C.c_double)]
+
+
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, _dp, C.c_int, _dp, _ip, _ip, C.c_int)
+
+
+class Comm(C.Structure):
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("allgather", ALLGATHER_FN), ("user", C.c_void_p)]
+
+
+class HadiError(RuntimeError):
+    def __init__(self, code, msg=""):
+        super().__init__("hadi error %d %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load libhadi.so (raises if it has not been built: there is no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise HadiError(ERR_CUDA, "libhadi.so is not built (run __graft_entry__.build())")
+        L = C.CDLL(LIB_PATH)
+        L.hadi_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        L.hadi_destroy.argtypes = [C.c_void_p]
+        L.hadi_destroy.restype = None
+        L.hadi_last_error.argtypes = [C.c_void_p]
+        L.hadi_last_error.restype = C.c_char_p
+        L.hadi_version.restype = C.c_char_p
+        L.hadi_kernel_launches.argtypes = [C.c_void_p]
+        L.hadi_kernel_launches.restype = C.c_longlong
+        L.hadi_price_batch.argtypes = [C.c_void_p, C.POINTER(Model), C.POINTER(Numerics), C.c_int,
+                                       C.POINTER(Point), _dp, _dp, _dp]
+        L.hadi_jacobian_batch.argtypes = [C.c_void_p, C.POINTER(Model), C.POINTER(Numerics), C.c_int,
+                                          C.POINTER(Point), C.c_double, _dp, _dp]
+        L.hadi_batch_create.argtypes = [C.c_void_p, C.POINTER(Model), C.POINTER(Numerics), C.c_int,
+                                        C.POINTER(Point), C.c_int, C.c_double, C.c_int, C.c_int,
+                                        C.POINTER(C.c_void_p)]
+        L.hadi_batch_num_items.argtypes = [C.c_void_p]
+        L.hadi_batch_launch.argtypes = [C.c_void_p]
+        L.hadi_batch_values_dev.argtypes = [C.c_void_p]
+        L.hadi_batch_values_dev.restype = C.c_void_p
+        L.hadi_batch_fetch.argtypes = [C.c_void_p, _dp]
+        L.hadi_batch_elapsed_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.hadi_batch_destroy.argtypes = [C.c_void_p]
+        L.hadi_batch_destroy.restype = None
+        L.hadi_jacobian_assemble.argtypes = [C.c_int, _dp, C.c_double, _dp, _dp]
+        L.hadi_partition.argtypes = [C.c_int, _ip, C.c_int, C.c_int, _ip, _ip]
+        L.hadi_item_costs.argtypes = [C.POINTER(Numerics), C.c_int, C.POINTER(Point), C.c_int, _ip]
+        L.hadi_solve5.argtypes = [_dp, _dp, _dp]
+        L.hadi_lm_update.argtypes = [C.c_int, _dp, _dp, C.c_double, _dp]
+        L.hadi_calibrate.argtypes = [C.c_void_p, C.POINTER(Model), C.POINTER(Numerics), C.c_int,
+                                     C.POINTER(Point), _dp, C.POINTER(LmOptions), C.POINTER(Comm),
+                                     C.POINTER(LmResult)]
+        L.hadi_grid.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _dp, _dp]
+        L.hadi_bs_call.argtypes = [C.c_double] * 5
+        L.hadi_bs_call.restype = C.c_double
+        _lib = L
+    return _lib
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def make_model(S0, V0, r_d, r_f, kappa, eta, sigma, rho):
+    return Model(S0, V0, r_d, r_f, kappa, eta, sigma, rho)
+
+
+def make_points(strikes, maturities, time_steps, delta_t=None):
+    """CalibrationPoint array; delta_t defaults to maturity / N as the reference computes it."""
+    strikes = np.atleast_1d(np.asarray(strikes, dtype=np.float64))
+    n = strikes.size
+    mats = np.broadcast_to(np.asarray(maturities, dtype=np.float64), (n,))
+    Ns = np.broadcast_to(np.asarray(time_steps, dtype=np.int64), (n,))
+    dts = mats / Ns if delta_t is None else np.broadcast_to(np.asarray(delta_t, dtype=np.float64), (n,))
+    pts = (Point * max(n, 1))()
+    for k in range(n):
+        pts[k] = Point(float(strikes[k]), float(mats[k]), int(Ns[k]), float(dts[k]), k)
+    return pts, n
+
+
+class _NumKeep:
+    """Numerics struct plus the numpy arrays its pointers refer to."""
+
+    def __init__(self, m1, m2, theta, style=EUROPEAN, payoff=CALL, scheme=DOUGLAS, divs=None):
+        if divs is not None and len(divs[0]) > 0:
+            self.arrs = [np.ascontiguousarray(x, dtype=np.float64) for x in divs]
+            nd = self.arrs[0].size
+            self.num = Numerics(m1, m2, theta, style, payoff, scheme, nd, _d(self.arrs[0]), _d(self.arrs[1]),
+                                _d(self.arrs[2]))
+        else:
+            self.arrs = []
+            self.num = Numerics(m1, m2, theta, style, payoff, scheme, 0, None, None, None)
+
+
+def make_numerics(m1, m2, theta, style=EUROPEAN, payoff=CALL, scheme=DOUGLAS, divs=None):
+    return _NumKeep(m1, m2, theta, style, payoff, scheme, divs)
+
+
+def grid(m1, m2, K, S0, V0):
+    s, v = np.zeros(m1 + 1), np.zeros(m2 + 1)
+    rc = lib().hadi_grid(m1, m2, K, S0, V0, _d(s), _d(v))
+    if rc != OK:
+        raise HadiError(rc)
+    return s, v
+
+
+def bs_call(S, K, r, vol, T):
+    return lib().hadi_bs_call(S, K, r, vol, T)
+
+
+def solve5(A, b):
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.zeros(5)
+    rc = lib().hadi_solve5(_d(A), _d(b), _d(x))
+    if rc != OK:
+        raise HadiError(rc)
+    return x
+
+
+def lm_update(J, r, lam):
+    J = np.ascontiguousarray(J, dtype=np.float64)
+    r = np.ascontiguousarray(r, dtype=np.float64)
+    delta = np.zeros(5)
+    rc = lib().hadi_lm_update(r.size, _d(J), _d(r), lam, _d(delta))
+    if rc != OK:
+        raise HadiError(rc)
+    return delta
+
+
+def partition(costs, world, rank):
+    costs = np.ascontiguousarray(costs, dtype=np.int32)
+    b, e = C.c_int(0), C.c_int(0)
+    rc = lib().hadi_partition(costs.size, costs.ctypes.data_as(_ip), world, rank, C.byref(b), C.byref(e))
+    if rc != OK:
+        raise HadiError(rc)
+    return b.value, e.value
+
+
+def item_costs(num, pts, n, mode):
+    nc = 6 if mode == MODE_JACOBIAN else 1
+    costs = np.zeros(max(n * nc, 1), dtype=np.int32)
+    rc = lib().hadi_item_costs(C.byref(num.num), n, pts, mode, costs.ctypes.data_as(_ip))
+    if rc != OK:
+        raise HadiError(rc)
+    return costs[:n * nc]
+
+
+def jacobian_assemble(values, eps):
+    values = np.ascontiguousarray(values, dtype=np.float64)
+    n = values.size // 6
+    J, base = np.zeros((n, 5)), np.zeros(n)
+    rc = lib().hadi_jacobian_assemble(n, _d(values), eps, _d(J), _d(base))
+    if rc != OK:
+        raise HadiError(rc)
+    return J, base
+
+
+class Context:
+    """hadi_ctx: one CUDA device, one stream."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = lib().hadi_create(C.byref(self._h), device)
+        if rc != OK:
+            self._h = None
+            raise HadiError(rc, "hadi_create failed (no usable CUDA device?)")
+
+    def close(self):
+        if self._h:
+            lib().hadi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != OK:
+            raise HadiError(rc, lib().hadi_last_error(self._h).decode())
+
+    @property
+    def kernel_launches(self):
+        return lib().hadi_kernel_launches(self._h)
+
+    def price_batch(self, model, num, pts, n, want_U=False, want_lambda=False):
+        P = (num.num.m1 + 1) * (num.num.m2 + 1)
+        prices = np.zeros(max(n, 1))
+        U = np.zeros((max(n, 1), P)) if want_U else None
+        lam = np.zeros((max(n, 1), P)) if want_lambda else None
+        self._check(lib().hadi_price_batch(self._h, C.byref(model), C.byref(num.num), n, pts, _d(prices), _d(U),
+                                           _d(lam)))
+        out = {"prices": prices[:n]}
+        if want_U:
+            out["U"] = U[:n]
+        if want_lambda:
+            out["lambda"] = lam[:n]
+        return out
+
+    def jacobian_batch(self, model, num, pts, n, eps=1e-6):
+        J, base = np.zeros((max(n, 1), 5)), np.zeros(max(n, 1))
+        self._check(lib().hadi_jacobian_batch(self._h, C.byref(model), C.byref(num.num), n, pts, eps, _d(J),
+                                              _d(base)))
+        return J[:n], base[:n]
+
+    def batch(self, model, num, pts, n, mode=MODE_PRICE, eps=1e-6, begin=0, end=-1):
+        return Batch(self, model, num, pts, n, mode, eps, begin, end)
+
+    def calibrate(self, model, num, pts, n, market, max_iter, tol, delta_tol, lambda0=0.01, eps=1e-6, comm=None):
+        market = np.ascontiguousarray(market, dtype=np.float64)
+        opt = LmOptions(max_iter, tol, delta_tol, lambda0, eps)
+        res = LmResult()
+        self._check(lib().hadi_calibrate(self._h, C.byref(model), C.byref(num.num), n, pts, _d(market),
+                                         C.byref(opt), None if comm is None else C.byref(comm), C.byref(res)))
+        return dict(params=list(res.params), final_error=res.final_error, lam=res.lambda_,
+                    delta_norm=res.delta_norm, iterations=res.iterations, converged=res.converged,
+                    pde_solves=res.pde_solves, gpu_ms=res.gpu_ms)
+
+
+class Batch:
+    """hadi_batch: descriptors and grids resident in HBM; launch() is asynchronous."""
+
+    def __init__(self, ctx, model, num, pts, n, mode, eps, begin, end):
+        self.ctx = ctx
+        self._keep = (model, num, pts)
+        self._h = C.c_void_p()
+        ctx._check(lib().hadi_batch_create(ctx._h, C.byref(model), C.byref(num.num), n, pts, mode, eps, begin, end,
+                                           C.byref(self._h)))
+        self.n_items = lib().hadi_batch_num_items(self._h)
+
+    def launch(self):
+        self.ctx._check(lib().hadi_batch_launch(self._h))
+
+    def fetch(self):
+        vals = np.zeros(max(self.n_items, 1))
+        self.ctx._check(lib().hadi_batch_fetch(self._h, _d(vals)))
+        return vals[:self.n_items]
+
+    def elapsed_ms(self):
+        ms = C.c_float(0.0)
+        self.ctx._check(lib().hadi_batch_elapsed_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def values_dev(self):
+        return lib().hadi_batch_values_dev(self._h)
+
+    def destroy(self):
+        if self._h:
+            lib().hadi_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass

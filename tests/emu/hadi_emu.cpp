@@ -1,0 +1,62 @@
+// TEST INFRASTRUCTURE — CPU emulation of the CUDA kernel's phase sequence.
+//
+// Compiles the product's device header (csrc/hadi_phases.cuh) with g++ and executes the phases of
+// hadi_douglas_kernel (csrc/hadi_kernel.cu) with a serial loop over thread ids in place of the CTA's
+// threads and __syncthreads().  It lets the CPU test-suite check the kernel's index logic and
+// operation order bit-for-bit against the oracle without a GPU.  Not shipped, not a fallback.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "hadi_phases.cuh"
+
+extern "C" int hadi_emu_solve(const HadiItem* item, int m1, int m2, int nt, const double* sg, const double* vg,
+                              const double* eg, int nd, const double* dd, const double* da, const double* dp,
+                              double* price, double* U_out, double* lam_out) {
+  HadiItem it = *item;
+  HadiView w;
+  w.m1 = m1; w.m2 = m2; w.ld = (m1 + 1) | 1; w.P = (m1 + 1) * (m2 + 1);
+  w.n1 = (m1 + 1 + 3) & ~3; w.n2 = (m2 + 1 + 3) & ~3; w.pj = (m2 + 1 + 3) & ~3;
+  const int rows = m2 + 1;
+  if (nt < m1 + 1 || nt - 1 <= m2) return -1;
+  std::vector<double> U(rows * w.ld, 1e300), Y(rows * w.ld, 1e300), ti(TI_COUNT * w.n1, 1e300), tj(TJ_COUNT * w.n2, 1e300);
+  std::vector<double> fM((m1 + 1) * w.pj, 1e300), fT((m1 + 1) * w.pj, 1e300), lam(rows * w.ld, 1e300);
+  std::vector<int> divk(w.n1, -7);
+  w.U = U.data(); w.Y = Y.data(); w.ti = ti.data(); w.tj = tj.data(); w.divk = divk.data();
+  w.fM = fM.data(); w.fT = fT.data(); w.lam = lam.data();
+  w.c = it.theta * it.dt;
+#define PHASE(call) for (int tid = 0; tid < nt; ++tid) { call; }
+  PHASE(hadi_phase_tables(it, w, sg, vg, tid, nt));
+  PHASE(hadi_phase_factor(it, w, vg, tid, nt, nt - 1));
+  {
+    const double* pay = hadi_ti(w, TI_PAY);
+    for (int p = 0; p < rows * (m1 + 1); ++p) {
+      const int j = p / (m1 + 1), i = p - j * (m1 + 1);
+      w.U[j * w.ld + i] = pay[i];
+      if (it.style == 1) w.lam[j * w.ld + i] = 0.0;
+    }
+  }
+  int div_cur = 0;
+  for (int n = 1; n <= it.N; ++n) {
+    if (it.nd > 0) {
+      const int hit = hadi_dividend_at(n, it.dt, nd, dd, div_cur);
+      if (hit >= 0) {
+        PHASE(hadi_phase_div1(w, da[hit], dp[hit], tid, nt));
+        PHASE(hadi_phase_div2(w, tid, nt));
+      }
+    }
+    const double e0 = eg[n - 1], e1 = eg[n];
+    PHASE(hadi_phase_explicit(it, w, e0, e1, tid, nt));
+    PHASE(hadi_phase_solve_a1(it, w, tid, nt));
+    PHASE(hadi_phase_solve_a2(it, w, e0, e1, tid, nt));
+    if (it.style == 1) PHASE(hadi_phase_project(it, w, tid, nt));
+  }
+  *price = w.U[it.idx_v * w.ld + it.idx_s];
+  for (int p = 0; p < w.P; ++p) {
+    const int j = p / (m1 + 1), i = p - j * (m1 + 1);
+    if (U_out) U_out[p] = w.U[j * w.ld + i];
+    if (lam_out) lam_out[p] = (it.style == 1) ? w.lam[j * w.ld + i] : 0.0;
+  }
+  return 0;
+}
+extern "C" int hadi_emu_item_size() { return (int)sizeof(HadiItem); }
