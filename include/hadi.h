@@ -144,6 +144,9 @@ double* hadi_batch_values_dev(hadi_batch* b);
 int hadi_batch_fetch(hadi_batch* b, double* values);
 /* elapsed device time of the last launch in ms (CUDA events on the context's stream) */
 int hadi_batch_elapsed_ms(hadi_batch* b, float* ms);
+/* development aid: per-phase SM cycle counters of the last launch (zeros unless built with
+ * -DHADI_PHASE_TIMING); out8[8] */
+int hadi_batch_phase_cycles(hadi_batch* b, long long* out8);
 void hadi_batch_destroy(hadi_batch* b);
 
 /* Jacobian assembly from the full [n*6] item values: base = v[6k], J[k][c] = (v[6k+1+c]-v[6k])/eps
@@ -175,6 +178,12 @@ typedef struct {
 int hadi_calibrate(hadi_ctx* ctx, const hadi_model* initial, const hadi_numerics* num, int n,
                    const hadi_point* points, const double* market_prices, const hadi_lm_options* opt,
                    const hadi_comm* comm, hadi_lm_result* result);
+
+/* ---- measurement ------------------------------------------------------------------------------ */
+/* FP64 issue-rate micro-benchmark on `device` (CUDA events): un-fused DMUL+DADD rate and DFMA rate in
+ * TFLOP/s, dependent-DADD latency in ns.  The un-fused rate is the roofline denominator of the
+ * SMEM-resident kernel (parity forbids FMA).  Any output pointer may be NULL. */
+int hadi_measure_fp64(int device, double* unfused_tflops, double* fma_tflops, double* dep_latency_ns);
 
 /* ---- host helpers restating small reference utilities ---------------------------------------- */
 /* Grid::Grid (src/grid.cpp:16-96) with the callers' constants; s[m1+1], v[m2+1] */

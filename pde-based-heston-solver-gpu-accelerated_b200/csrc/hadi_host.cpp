@@ -38,7 +38,7 @@ struct DevBuf {
 struct hadi_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
-  int threads = 0, max_smem = 0, sm_count = 0;
+  int sm_count = 0;
   std::string err;
   long long launches = 0;
   std::vector<DevBuf> pool;  // caching allocator: device and pinned-host blocks are reused across batches
@@ -53,8 +53,8 @@ struct hadi_batch {
   int n_items = 0;
   int m1 = 0, m2 = 0;
   HadiLaunch L{};
+  HadiPlan plan{};
   int grid_ctas = 0;
-  size_t smem = 0;
   std::vector<int> bufs;  // indices into ctx->pool owned by this batch
   double* h_values = nullptr;  // pinned
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -175,6 +175,7 @@ Geometry geometry(int m1, int m2) {
 bool valid_numerics(const hadi_numerics* num) {
   if (!num) return false;
   if (num->m1 < 4 || num->m2 < 4 || num->m1 > 4096 || num->m2 > 4096) return false;
+  if (num->m2 > num->m1) return false;  // b1 lands on node (j, m1-j) only while m2 <= m1 (every reference caller: m1 = 2*m2)
   if (num->style != HADI_EUROPEAN && num->style != HADI_AMERICAN) return false;
   if (num->payoff != HADI_CALL && num->payoff != HADI_PUT) return false;
   if (num->num_dividends < 0) return false;
@@ -206,7 +207,7 @@ int hadi_create(hadi_ctx** out, int device) {
     delete ctx;
     return HADI_ERR_CUDA;
   }
-  if (hadi_douglas_config(&ctx->threads, &ctx->max_smem, &ctx->sm_count, device) != 0) {
+  if (cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return HADI_ERR_CUDA;
@@ -309,9 +310,12 @@ int hadi_batch_create(hadi_ctx* ctx, const hadi_model* model, const hadi_numeric
   const Geometry g = geometry(num->m1, num->m2);
   const int m1 = g.m1, m2 = g.m2;
   const int P = (m1 + 1) * (m2 + 1);
-  const size_t smem = hadi_smem_bytes(m1, m2, g.ld, g.n1, g.n2);
-  if (smem > (size_t)ctx->max_smem) return fail(ctx, HADI_ERR_SMEM, "grid does not fit in shared memory");
-  if (ctx->threads < m1 + 1 || ctx->threads - 1 <= m2) return fail(ctx, HADI_ERR_SMEM, "grid wider than the CTA");
+  HadiPlan plan;
+  {
+    const int prc = hadi_douglas_plan(ctx->device, m1, m2, g.ld, g.n1, g.n2, g.pj, &plan);
+    if (prc < 0) return fail(ctx, HADI_ERR_SMEM, "grid does not fit the shared-memory resident kernel");
+    if (prc > 0) return cuda_fail(ctx, (cudaError_t)prc, "kernel plan");
+  }
 
   std::unique_ptr<hadi_batch> b(new hadi_batch());
   b->ctx = ctx;
@@ -419,9 +423,8 @@ int hadi_batch_create(hadi_ctx* ctx, const hadi_model* model, const hadi_numeric
   double* d_values = (double*)take(sizeof(double) * (size_t)std::max(n_items, 1), false);
   int* d_counter = (int*)take(256, false);
 
-  int occ = 2;
-  if (2 * (smem + 1024) > (size_t)228 * 1024) occ = 1;
-  b->grid_ctas = std::max(1, std::min(n_items, occ * ctx->sm_count));
+  b->plan = plan;
+  b->grid_ctas = std::max(1, std::min(n_items, plan.ctas_per_sm * plan.sm_count));
   const size_t stride = (hadi_scratch_doubles(m1, m2, g.ld, g.pj) + 31) & ~size_t(31);
   double* d_scratch = (double*)take(sizeof(double) * stride * (size_t)b->grid_ctas, false);
   if (!h_stage || !d_stage || !b->h_values || !d_values || !d_counter || !d_scratch) {
@@ -470,7 +473,8 @@ int hadi_batch_create(hadi_ctx* ctx, const hadi_model* model, const hadi_numeric
   L.out_values = d_values;
   L.out_U = nullptr;
   L.out_lam = nullptr;
-  b->smem = smem;
+  L.prof = (long long*)take(sizeof(long long) * 8 * (size_t)b->grid_ctas, false);
+  if (L.prof) cudaMemsetAsync(L.prof, 0, sizeof(long long) * 8 * (size_t)b->grid_ctas, ctx->stream);
   if (cudaEventCreate(&b->ev0) != cudaSuccess || cudaEventCreate(&b->ev1) != cudaSuccess) {
     release_all();
     return cuda_fail(ctx, cudaGetLastError(), "event");
@@ -490,7 +494,7 @@ int hadi_batch_launch(hadi_batch* b) {
   if (e != cudaSuccess) return cuda_fail(ctx, e, "memset");
   cudaEventRecord(b->ev0, ctx->stream);
   if (b->n_items > 0) {
-    const int rc = hadi_launch_douglas(b->L, b->grid_ctas, b->smem, ctx->stream);
+    const int rc = hadi_launch_douglas(b->L, b->plan, b->grid_ctas, ctx->stream);
     if (rc != 0) return cuda_fail(ctx, (cudaError_t)rc, "kernel launch");
     ctx->launches++;
   }
@@ -519,6 +523,22 @@ int hadi_batch_elapsed_ms(hadi_batch* b, float* ms) {
   if (e != cudaSuccess) return cuda_fail(b->ctx, e, "event sync");
   e = cudaEventElapsedTime(ms, b->ev0, b->ev1);
   if (e != cudaSuccess) return cuda_fail(b->ctx, e, "event elapsed");
+  return HADI_OK;
+}
+
+// Phase cycle counters of the last launch summed over CTAs (all zero unless the library was built
+// with -DHADI_PHASE_TIMING): [0] set-up, [1] dividend jump, [2] explicit stage, [3] A1 solves,
+// [4] A2 solves, [5] projection, [6] output, [7] item fetch.  Development aid.
+int hadi_batch_phase_cycles(hadi_batch* b, long long* out8) {
+  if (!b || !out8 || !b->L.prof) return HADI_ERR_ARG;
+  cudaSetDevice(b->ctx->device);
+  cudaStreamSynchronize(b->ctx->stream);
+  std::vector<long long> h((size_t)8 * b->grid_ctas);
+  if (cudaMemcpy(h.data(), b->L.prof, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return cuda_fail(b->ctx, cudaGetLastError(), "D2H prof");
+  for (int k = 0; k < 8; ++k) out8[k] = 0;
+  for (int c = 0; c < b->grid_ctas; ++c)
+    for (int k = 0; k < 8; ++k) out8[k] += h[(size_t)c * 8 + k];
   return HADI_OK;
 }
 

@@ -3,8 +3,10 @@
 // One CTA solves one work item (an option or one Jacobian bump) from payoff to price without
 // leaving the SM: the solution U and the stage vector Y stay in shared memory for all N time steps;
 // the explicit A0/A1/A2 products, both implicit line solves, the boundary terms, the dividend jump
-// and the American projection are fused between __syncthreads().  CTAs are persistent and pull
-// items from a global counter (longest items first), so a batch of any size runs as one launch.
+// and the American projection are fused into three barrier-separated phases per step.  CTAs are
+// persistent and pull items from a global counter (longest items first), so a batch of any size
+// runs as one launch; two CTAs share an SM so that one option's latency-bound line solves overlap
+// the other's throughput-bound explicit stage.
 //
 // Replaces the reference's "Base_Price_computation" / "Jacobian_computation" Kokkos kernels
 // (src/jacobian_computation.cpp:232,391,...; src/heston_calibration.cpp:2206,2366) together with
@@ -13,34 +15,159 @@
 // Compile with -fmad=false: parity with the reference requires un-fused multiplies and adds.
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <type_traits>
 
 #include "hadi_launch.h"
 
-#ifndef HADI_NT
-#define HADI_NT 384
-#endif
-
 namespace {
 
-template <int NT>
-__global__ void __launch_bounds__(NT, 2) hadi_douglas_kernel(const HadiLaunch L) {
+#ifdef HADI_PHASE_TIMING
+#define HADI_TICK(k) { const long long tn = clock64(); tacc[k] += tn - tlast; tlast = tn; }
+#else
+#define HADI_TICK(k)
+#endif
+
+// One item, payoff to price.  Returns (CTA-uniform) whether any guarded division left its fast-path
+// range; EXACT = true compiles every division as IEEE '/'.
+template <int NT, int M1, int M2, bool EXACT, class Feed>
+__device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiItem& it, HadiView& w, Feed& feed,
+                                                int tid, long long* tacc, long long& tlast) {
+  const int m1 = M1 ? M1 : L.m1, m2 = M2 ? M2 : L.m2;
+  const double* sg = L.s_pool + it.s_off;
+  const double* vg = L.v_pool + it.v_off;
+  const double* eg = L.e_pool + it.e_off;
+  w.c = it.theta * it.dt;
+  const double rdt = hadi_rcp_prep(it.dt);
+  unsigned bad = 0;
+
+  hadi_phase_tables(it, w, sg, vg, tid, NT);
+  __syncthreads();
+  hadi_phase_factor(it, w, vg, tid, NT, NT - 1);
+  if constexpr (!std::is_same<Feed, HadiDirectFeed>::value) {
+    // the factor streams were written with generic stores and will be read by TMA (async proxy)
+    __threadfence();
+    asm volatile("fence.proxy.async;" ::: "memory");
+  }
+  __syncthreads();  // the A2 assembly keeps scratch tables in Y: finish it before Y is initialised
+  // initial condition U = payoff (the reference's U_0 input array), lambda = 0
+  {
+    const HadiMap mp = hadi_map(m1, m2, tid, NT);
+    if (mp.active) {
+      const double pay = hadi_ti(w, TI_PAY)[mp.i];
+      for (int j = mp.j0; j < mp.j1; ++j) {
+        w.U[j * w.ld + mp.i] = pay;
+        if (it.style == 1) {
+          w.lam[j * w.ld + mp.i] = 0.0;
+          w.Y[j * w.ld + mp.i] = 0.0;   // phase E reads lambda from Y
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if constexpr (!std::is_same<Feed, HadiDirectFeed>::value) {
+    if (feed.producer(tid)) feed.produce(0, it.N, 0);  // first chunks are in flight before step 1
+  }
+  HADI_TICK(0)
+
+  int div_cur = 0;
+  for (int n = 1; n <= it.N; ++n) {
+    if (it.nd > 0) {
+      const int hit = hadi_dividend_at(n, it.dt, it.nd, L.div_dates, div_cur);
+      if (hit >= 0) {  // uniform across the CTA
+        hadi_phase_div1(w, L.div_amounts[hit], L.div_pcts[hit], tid, NT);
+        __syncthreads();
+        hadi_phase_div2(w, tid, NT);
+        __syncthreads();
+        if (it.style == 1) {
+          hadi_phase_div3(w, tid, NT);
+          __syncthreads();
+        }
+      }
+    }
+    HADI_TICK(0)
+    const double e0 = eg[n - 1], e1 = eg[n];
+    hadi_phase_explicit<M1, M2>(it, w, e0, e1, tid, NT);
+    __syncthreads();
+    HADI_TICK(2)
+    hadi_phase_solve_a1<M1, M2, EXACT>(it, w, e0, e1, n, tid, NT, feed, bad, &tacc[1]);
+    __syncthreads();
+    HADI_TICK(3)
+    hadi_phase_rhs2<M1, M2>(it, w, e0, e1, tid, NT);
+    __syncthreads();
+    HADI_TICK(7)
+    hadi_phase_solve_a2<M1, M2, EXACT>(it, w, tid, NT, bad);
+    __syncthreads();
+    HADI_TICK(4)
+    if (it.style == 1) {
+      hadi_phase_project<M1, M2, EXACT>(it, w, rdt, tid, NT, bad);
+      __syncthreads();
+    }
+    HADI_TICK(5)
+  }
+  if constexpr (!std::is_same<Feed, HadiDirectFeed>::value) {
+    // every chunk issued for this item has been consumed; keep both counters in step on all threads
+    const unsigned nc = (unsigned)(feed.ncf() + feed.ncb());
+    feed.issued = feed.consumed = feed.base = feed.base + (unsigned)it.N * nc;
+  }
+  return __syncthreads_or((int)bad) != 0;
+}
+
+template <int NT, int MINB, int M1, int M2, bool RING>
+__global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch L) {
   extern __shared__ double smem[];
   __shared__ int s_item;
   const int tid = threadIdx.x;
+  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tlast = 0;
+#ifdef HADI_PHASE_TIMING
+  tlast = clock64();
+#endif
 
+  const int m1 = M1 ? M1 : L.m1, m2 = M2 ? M2 : L.m2;
   HadiView w;
-  w.m1 = L.m1; w.m2 = L.m2; w.ld = L.ld; w.P = (L.m1 + 1) * (L.m2 + 1);
-  w.n1 = L.n1; w.n2 = L.n2; w.pj = L.pj;
-  const int rows = L.m2 + 1;
-  w.U = smem;
-  w.Y = w.U + rows * L.ld;
-  w.ti = w.Y + rows * L.ld;
-  w.tj = w.ti + TI_COUNT * L.n1;
-  w.divk = reinterpret_cast<int*>(w.tj + TJ_COUNT * L.n2);
+  w.m1 = m1; w.m2 = m2; w.P = (m1 + 1) * (m2 + 1);
+  w.ld = hadi_geo_ld(m1); w.n1 = hadi_geo_n1(m1); w.n2 = hadi_geo_n2(m2); w.pj = hadi_geo_pj(m2);
+  const HadiSmemLayout lay = hadi_smem_layout(m1, m2, w.ld, w.n1, w.n2, w.pj, RING);
+  char* sbase = reinterpret_cast<char*>(smem);
+  double* Ualloc = reinterpret_cast<double*>(sbase + lay.U);
+  w.U = Ualloc + HADI_HALO * w.ld + 1;
+  w.Y = reinterpret_cast<double*>(sbase + lay.Y);
+  w.ti = reinterpret_cast<double*>(sbase + lay.ti);
+  w.tj = reinterpret_cast<double*>(sbase + lay.tj);
+  w.divk = reinterpret_cast<int*>(sbase + lay.divk);
   double* scratch = L.scratch + (size_t)blockIdx.x * L.scratch_stride;
   w.fM = scratch;
-  w.fT = w.fM + (size_t)(L.m1 + 1) * L.pj;
-  w.lam = w.fT + (size_t)(L.m1 + 1) * L.pj;
+  w.fB = w.fM + (size_t)m1 * w.pj;
+  w.lam = w.fB + (size_t)m1 * 2 * w.pj;
+  // zero the halo of U once (payoff initialisation and the sweeps only ever write rows 0..m2)
+  for (int k = tid; k < (m2 + 1 + 2 * HADI_HALO) * w.ld + 2; k += NT) Ualloc[k] = 0.0;
+
+  // factor feed of phase S1
+  const int ncw = (m2 + 1 + 31) / 32;  // solver warps
+  typename std::conditional<RING, HadiRingFeed, HadiDirectFeed>::type feed;
+  feed.fM = w.fM;
+  feed.fB = w.fB;
+  feed.pj = w.pj;
+  if constexpr (RING) {
+    feed.m1 = m1;
+    feed.prod_tid = 32 * ncw;
+    feed.ring = reinterpret_cast<double*>(sbase + lay.ring);
+    feed.full = reinterpret_cast<unsigned long long*>(sbase + lay.bars);
+    feed.empty = feed.full + HADI_NS;
+    feed.issued = feed.consumed = feed.base = 0;
+#ifdef HADI_PHASE_TIMING
+    feed.wait_cycles = 0;
+#endif
+    feed.probe = 0;
+    if (tid == 0) {
+      for (int k = 0; k < HADI_NS; ++k) {
+        hadi_mbar_init(&feed.full[k], 1);
+        hadi_mbar_init(&feed.empty[k], m2 + 1);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
+  __syncthreads();
 
   for (;;) {
     if (tid == 0) s_item = atomicAdd(L.counter, 1);
@@ -48,84 +175,105 @@ __global__ void __launch_bounds__(NT, 2) hadi_douglas_kernel(const HadiLaunch L)
     const int item = s_item;
     if (item >= L.n_items) break;
     const HadiItem it = L.items[item];
-    const double* sg = L.s_pool + it.s_off;
-    const double* vg = L.v_pool + it.v_off;
-    const double* eg = L.e_pool + it.e_off;
-    w.c = it.theta * it.dt;
+    HADI_TICK(0)
+    // fast pass; if any guarded division left its range (never observed on option data), the item is
+    // re-solved with IEEE divisions so that the published value is exact in every case
+    if (hadi_solve_item<NT, M1, M2, false>(L, it, w, feed, tid, tacc, tlast))
+      hadi_solve_item<NT, M1, M2, true>(L, it, w, feed, tid, tacc, tlast);
 
-    hadi_phase_tables(it, w, sg, vg, tid, NT);
-    __syncthreads();
-    hadi_phase_factor(it, w, vg, tid, NT, NT - 1);
-    // initial condition U = payoff (the reference's U_0 input array), lambda = 0
-    {
-      const double* pay = hadi_ti(w, TI_PAY);
-      for (int p = tid; p < rows * (L.m1 + 1); p += NT) {
-        const int j = p / (L.m1 + 1), i = p - j * (L.m1 + 1);
-        w.U[j * L.ld + i] = pay[i];
-        if (it.style == 1) w.lam[j * L.ld + i] = 0.0;
-      }
-    }
-    __syncthreads();
-
-    int div_cur = 0;
-    for (int n = 1; n <= it.N; ++n) {
-      if (it.nd > 0) {
-        const int hit = hadi_dividend_at(n, it.dt, it.nd, L.div_dates, div_cur);
-        if (hit >= 0) {  // uniform across the CTA
-          hadi_phase_div1(w, L.div_amounts[hit], L.div_pcts[hit], tid, NT);
-          __syncthreads();
-          hadi_phase_div2(w, tid, NT);
-          __syncthreads();
+    if (tid == 0) L.out_values[it.out] = w.U[it.idx_v * w.ld + it.idx_s];
+    if (L.out_U != nullptr || L.out_lam != nullptr) {
+      const HadiMap mp = hadi_map(m1, m2, tid, NT);
+      if (mp.active) {
+        for (int j = mp.j0; j < mp.j1; ++j) {
+          const size_t p = (size_t)it.out * w.P + (size_t)j * (m1 + 1) + mp.i;
+          if (L.out_U != nullptr) L.out_U[p] = w.U[j * w.ld + mp.i];
+          if (L.out_lam != nullptr && it.style == 1) L.out_lam[p] = w.lam[j * w.ld + mp.i];
         }
-      }
-      const double e0 = eg[n - 1], e1 = eg[n];
-      hadi_phase_explicit(it, w, e0, e1, tid, NT);
-      __syncthreads();
-      hadi_phase_solve_a1(it, w, tid, NT);
-      __syncthreads();
-      hadi_phase_solve_a2(it, w, e0, e1, tid, NT);
-      __syncthreads();
-      if (it.style == 1) {
-        hadi_phase_project(it, w, tid, NT);
-        __syncthreads();
-      }
-    }
-
-    if (tid == 0) L.out_values[it.out] = w.U[it.idx_v * L.ld + it.idx_s];
-    if (L.out_U != nullptr) {
-      double* dst = L.out_U + (size_t)it.out * w.P;
-      for (int p = tid; p < w.P; p += NT) {
-        const int j = p / (L.m1 + 1), i = p - j * (L.m1 + 1);
-        dst[p] = w.U[j * L.ld + i];
-      }
-    }
-    if (L.out_lam != nullptr && it.style == 1) {
-      double* dst = L.out_lam + (size_t)it.out * w.P;
-      for (int p = tid; p < w.P; p += NT) {
-        const int j = p / (L.m1 + 1), i = p - j * (L.m1 + 1);
-        dst[p] = w.lam[j * L.ld + i];
       }
     }
     __syncthreads();  // everyone is done with s_item, U and the tables before the next item
+    HADI_TICK(6)
   }
+#ifdef HADI_PHASE_TIMING
+  if constexpr (RING) tacc[6] = feed.wait_cycles;   // slot 6 reports the ring wait of solver thread 0
+  if (tid == 0 && L.prof != nullptr)
+    for (int k = 0; k < 8; ++k) L.prof[(size_t)blockIdx.x * 8 + k] = tacc[k];
+#endif
 }
+
+// ---- variants ----------------------------------------------------------------------------------
+// 0: 101 x 51 nodes (BASELINE configs 1, 2, 5): 320 threads = 3 row-chunks x 101 columns (+17),
+//    2 CTAs/SM, <= 102 registers (no spills: L1 is all but gone at this shared-memory carve-out)
+// 1:  51 x 26 nodes (the reference's own test / benchmark grid): 256 threads = 5 x 51 (+1), 3 CTAs/SM
+// 2: any grid with m1+1 <= 416 that fits shared memory, run-time dimensions, direct factor loads
+// 3: any grid with m1+1 <= 1024 that fits shared memory, run-time dimensions, one CTA per SM
+#define HADI_VARIANTS(X)        \
+  X(0, 320, 2, 100, 50, true)  \
+  X(1, 256, 3, 50, 25, true)   \
+  X(2, 416, 2, 0, 0, false)    \
+  X(3, 1024, 1, 0, 0, false)
+
+struct VariantInfo {
+  int threads, m1, m2;
+  bool ring;
+  const void* fn;
+};
+const VariantInfo* variants() {
+  static const VariantInfo v[] = {
+#define X(id, nt, minb, a, b, r) {nt, a, b, r, (const void*)hadi_douglas_kernel<nt, minb, a, b, r>},
+      HADI_VARIANTS(X)
+#undef X
+  };
+  return v;
+}
+constexpr int kNumVariants = 4;
 
 }  // namespace
 
-int hadi_douglas_config(int* threads, int* max_smem_optin, int* sm_count, int device) {
-  int v = 0;
-  if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess) return -1;
-  *max_smem_optin = v;
-  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
-  *sm_count = v;
-  *threads = HADI_NT;
+int hadi_douglas_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj, HadiPlan* plan) {
+  int max_smem = 0, sms = 0;
+  cudaError_t e = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  if (e != cudaSuccess) return (int)e;
+  const VariantInfo* v = variants();
+  int pick = -1;
+  size_t smem = 0;
+  for (int k = 0; k < kNumVariants; ++k) {
+    if (v[k].m1 != 0 && (v[k].m1 != m1 || v[k].m2 != m2)) continue;
+    if (v[k].threads < m1 + 1 || v[k].threads - 1 <= m2) continue;
+    smem = hadi_smem_layout(m1, m2, ld, n1, n2, pj, v[k].ring).total;
+    if (smem > (size_t)max_smem) continue;
+    pick = k;
+    break;
+  }
+  if (pick < 0) return -1;
+  e = cudaFuncSetAttribute(v[pick].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v[pick].fn, v[pick].threads, smem);
+  if (e != cudaSuccess) return (int)e;
+  if (occ < 1) return -1;
+  plan->variant = pick;
+  plan->threads = v[pick].threads;
+  plan->ctas_per_sm = occ;
+  plan->sm_count = sms;
+  plan->smem_bytes = smem;
   return 0;
 }
 
-int hadi_launch_douglas(const HadiLaunch& L, int grid_ctas, size_t smem_bytes, void* stream) {
-  cudaError_t e = cudaFuncSetAttribute(hadi_douglas_kernel<HADI_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem_bytes);
-  if (e != cudaSuccess) return (int)e;
-  hadi_douglas_kernel<HADI_NT><<<grid_ctas, HADI_NT, smem_bytes, (cudaStream_t)stream>>>(L);
+int hadi_launch_douglas(const HadiLaunch& L, const HadiPlan& plan, int grid_ctas, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (plan.variant) {
+#define X(id, nt, minb, a, b, r) \
+  case id:                       \
+    hadi_douglas_kernel<nt, minb, a, b, r><<<grid_ctas, nt, plan.smem_bytes, st>>>(L); \
+    break;
+    HADI_VARIANTS(X)
+#undef X
+    default:
+      return (int)cudaErrorInvalidValue;
+  }
   return (int)cudaGetLastError();
 }

@@ -20,18 +20,45 @@ struct HadiLaunch {
   double* out_values;        // [n_items] price at (S0, V0) per item (slot item.out)
   double* out_U;             // optional [n_items][P] natural layout
   double* out_lam;           // optional [n_items][P]
+  long long* prof;           // optional [gridDim.x][8] phase cycle counters (HADI_PHASE_TIMING builds only)
 };
 
-// shared memory (bytes) the Douglas kernel needs for a grid
-inline size_t hadi_smem_bytes(int m1, int m2, int ld, int n1, int n2) {
+// Kernel variant chosen for a grid shape (hadi_kernel.cu).
+struct HadiPlan {
+  int variant;        // index of the template instantiation
+  int threads;        // CTA size
+  int ctas_per_sm;    // resident CTAs per SM at this shared-memory footprint
+  int sm_count;
+  size_t smem_bytes;  // dynamic shared memory per CTA
+};
+
+// shared memory layout of the Douglas kernel (offsets in bytes from the dynamic smem base)
+struct HadiSmemLayout {
+  size_t U, Y, ti, tj, divk, ring, bars, total;
+};
+HADI_HD HadiSmemLayout hadi_smem_layout(int m1, int m2, int ld, int n1, int n2, int pj, bool ring) {
   (void)m1;
-  size_t d = (size_t)2 * (size_t)(m2 + 1) * (size_t)ld + (size_t)TI_COUNT * (size_t)n1 + (size_t)TJ_COUNT * (size_t)n2;
-  return d * sizeof(double) + (size_t)n1 * sizeof(int) + 16;
+  HadiSmemLayout s;
+  size_t off = 0;
+  // U carries HADI_HALO zero rows above and below and one spare word at either end
+  s.U = off; off += sizeof(double) * ((size_t)(m2 + 1 + 2 * HADI_HALO) * ld + 2);
+  s.Y = off; off += sizeof(double) * (size_t)(m2 + 1) * ld;
+  s.ti = off; off += sizeof(double) * (size_t)TI_COUNT * n1;
+  s.tj = off; off += sizeof(double) * (size_t)TJ_COUNT * n2;
+  s.divk = off; off += sizeof(int) * (size_t)n1;
+  off = (off + 127) & ~size_t(127);
+  s.ring = off;
+  if (ring) off += sizeof(double) * (size_t)HADI_NS * HADI_KF * pj;
+  s.bars = off;
+  if (ring) off += sizeof(unsigned long long) * 2 * HADI_NS;
+  s.total = off + 16;
+  return s;
 }
+// per-CTA global scratch: fM [m1][pj], fB [m1][2*pj], lambda [m2+1][ld]
 inline size_t hadi_scratch_doubles(int m1, int m2, int ld, int pj) {
-  return (size_t)2 * (size_t)(m1 + 1) * (size_t)pj + (size_t)(m2 + 1) * (size_t)ld;
+  return (size_t)3 * (size_t)m1 * (size_t)pj + (size_t)(m2 + 1) * (size_t)ld;
 }
 
-// defined in hadi_kernel.cu
-int hadi_launch_douglas(const HadiLaunch& L, int grid_ctas, size_t smem_bytes, void* stream);
-int hadi_douglas_config(int* threads, int* max_smem_optin, int* sm_count, int device);
+// defined in hadi_kernel.cu; return 0 or a cudaError_t
+int hadi_douglas_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj, HadiPlan* plan);
+int hadi_launch_douglas(const HadiLaunch& L, const HadiPlan& plan, int grid_ctas, void* stream);

@@ -15,25 +15,33 @@ extern "C" int hadi_emu_solve(const HadiItem* item, int m1, int m2, int nt, cons
                               double* price, double* U_out, double* lam_out) {
   HadiItem it = *item;
   HadiView w;
-  w.m1 = m1; w.m2 = m2; w.ld = (m1 + 1) | 1; w.P = (m1 + 1) * (m2 + 1);
-  w.n1 = (m1 + 1 + 3) & ~3; w.n2 = (m2 + 1 + 3) & ~3; w.pj = (m2 + 1 + 3) & ~3;
+  w.m1 = m1; w.m2 = m2; w.ld = hadi_geo_ld(m1); w.P = (m1 + 1) * (m2 + 1);
+  w.n1 = hadi_geo_n1(m1); w.n2 = hadi_geo_n2(m2); w.pj = hadi_geo_pj(m2);
   const int rows = m2 + 1;
   if (nt < m1 + 1 || nt - 1 <= m2) return -1;
-  std::vector<double> U(rows * w.ld, 1e300), Y(rows * w.ld, 1e300), ti(TI_COUNT * w.n1, 1e300), tj(TJ_COUNT * w.n2, 1e300);
-  std::vector<double> fM((m1 + 1) * w.pj, 1e300), fT((m1 + 1) * w.pj, 1e300), lam(rows * w.ld, 1e300);
+  std::vector<double> U((rows + 2 * HADI_HALO) * w.ld + 2, 0.0), Y(rows * w.ld, 1e300), ti(TI_COUNT * w.n1, 1e300), tj(TJ_COUNT * w.n2, 1e300);
+  std::vector<double> fM(m1 * w.pj, 1e300), fB(m1 * 2 * w.pj, 1e300), lam(rows * w.ld, 1e300);
   std::vector<int> divk(w.n1, -7);
-  w.U = U.data(); w.Y = Y.data(); w.ti = ti.data(); w.tj = tj.data(); w.divk = divk.data();
-  w.fM = fM.data(); w.fT = fT.data(); w.lam = lam.data();
+  w.U = U.data() + HADI_HALO * w.ld + 1; w.Y = Y.data(); w.ti = ti.data(); w.tj = tj.data(); w.divk = divk.data();
+  w.fM = fM.data(); w.fB = fB.data(); w.lam = lam.data();
+  HadiDirectFeed feed;
+  feed.fM = w.fM; feed.fB = w.fB; feed.pj = w.pj;
   w.c = it.theta * it.dt;
+  const double rdt = hadi_rcp_prep(it.dt);
+  const bool spec = true;
+  unsigned bad = 0;
 #define PHASE(call) for (int tid = 0; tid < nt; ++tid) { call; }
   PHASE(hadi_phase_tables(it, w, sg, vg, tid, nt));
   PHASE(hadi_phase_factor(it, w, vg, tid, nt, nt - 1));
   {
-    const double* pay = hadi_ti(w, TI_PAY);
-    for (int p = 0; p < rows * (m1 + 1); ++p) {
-      const int j = p / (m1 + 1), i = p - j * (m1 + 1);
-      w.U[j * w.ld + i] = pay[i];
-      if (it.style == 1) w.lam[j * w.ld + i] = 0.0;
+    for (int tid = 0; tid < nt; ++tid) {
+      const HadiMap mp = hadi_map(m1, m2, tid, nt);
+      if (!mp.active) continue;
+      const double pay = hadi_ti(w, TI_PAY)[mp.i];
+      for (int j = mp.j0; j < mp.j1; ++j) {
+        w.U[j * w.ld + mp.i] = pay;
+        if (it.style == 1) { w.lam[j * w.ld + mp.i] = 0.0; w.Y[j * w.ld + mp.i] = 0.0; }
+      }
     }
   }
   int div_cur = 0;
@@ -43,13 +51,23 @@ extern "C" int hadi_emu_solve(const HadiItem* item, int m1, int m2, int nt, cons
       if (hit >= 0) {
         PHASE(hadi_phase_div1(w, da[hit], dp[hit], tid, nt));
         PHASE(hadi_phase_div2(w, tid, nt));
+        if (it.style == 1) PHASE(hadi_phase_div3(w, tid, nt));
       }
     }
     const double e0 = eg[n - 1], e1 = eg[n];
-    PHASE(hadi_phase_explicit(it, w, e0, e1, tid, nt));
-    PHASE(hadi_phase_solve_a1(it, w, tid, nt));
-    PHASE(hadi_phase_solve_a2(it, w, e0, e1, tid, nt));
-    if (it.style == 1) PHASE(hadi_phase_project(it, w, tid, nt));
+    if (spec && m1 == 100 && m2 == 50) {
+      PHASE((hadi_phase_explicit<100, 50>(it, w, e0, e1, tid, nt)));
+      PHASE((hadi_phase_solve_a1<100, 50, true>(it, w, e0, e1, n, tid, nt, feed, bad)));
+      PHASE((hadi_phase_rhs2<100, 50>(it, w, e0, e1, tid, nt)));
+      PHASE((hadi_phase_solve_a2<100, 50, true>(it, w, tid, nt, bad)));
+      if (it.style == 1) PHASE((hadi_phase_project<100, 50, true>(it, w, rdt, tid, nt, bad)));
+    } else {
+      PHASE((hadi_phase_explicit<0, 0>(it, w, e0, e1, tid, nt)));
+      PHASE((hadi_phase_solve_a1<0, 0, true>(it, w, e0, e1, n, tid, nt, feed, bad)));
+      PHASE((hadi_phase_rhs2<0, 0>(it, w, e0, e1, tid, nt)));
+      PHASE((hadi_phase_solve_a2<0, 0, true>(it, w, tid, nt, bad)));
+      if (it.style == 1) PHASE((hadi_phase_project<0, 0, true>(it, w, rdt, tid, nt, bad)));
+    }
   }
   *price = w.U[it.idx_v * w.ld + it.idx_s];
   for (int p = 0; p < w.P; ++p) {
