@@ -117,6 +117,8 @@ const char* hadi_last_error(const hadi_ctx* ctx);
 const char* hadi_version(void);
 /* number of hadi kernels launched by this context so far (bench.py's gpu_launches) */
 long long hadi_kernel_launches(const hadi_ctx* ctx);
+/* cumulative host->device / device->host bytes moved by this context */
+int hadi_transfer_bytes(const hadi_ctx* ctx, long long* h2d, long long* d2h);
 
 /* ---- one-call entry points (host buffers in, host buffers out; synchronous) ------------------- */
 /* prices[n]; U_out[n*(m1+1)*(m2+1)] and lambda_out (same shape) may be NULL. */

@@ -1,0 +1,184 @@
+"""TEST INFRASTRUCTURE — generates tests/golden/*.json from the REAL reference.
+
+The numbers are produced by oracle/_ref/libhadi_ref.so, i.e. by the reference's own unmodified
+sources (see oracle/ref_driver.cpp).  Run it in the build container, where /root/reference is
+mounted:   make -C oracle ref && python oracle/make_golden.py
+The fixtures are committed; the GPU box never needs /root/reference.
+
+Floats are written with repr(), which round-trips IEEE doubles exactly.
+"""
+import hashlib
+import json
+import math
+import os
+import struct
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+from oracle.reflib import RefLib  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+BASE = dict(S0=100.0, V0=0.04, r_d=0.025, r_f=0.0, rho=-0.9, sigma=0.3, kappa=1.5, eta=0.04, theta=0.8)
+DIVS = ([0.2, 0.4, 0.6, 0.8], [0.5, 0.3, 0.2, 0.1], [0.02, 0.02, 0.02, 0.02])
+
+
+def digest(a):
+    """sha256 of the raw little-endian doubles, with -0.0 normalised to +0.0 (signed zeros are not
+    part of the parity contract, SURVEY hard part 8)."""
+    a = np.ascontiguousarray(a, dtype=np.float64) + 0.0
+    return hashlib.sha256(a.tobytes()).hexdigest()
+
+
+def main():
+    R = RefLib()
+    os.makedirs(OUT, exist_ok=True)
+
+    # ---- grids (src/grid.cpp:16-96)
+    grids = []
+    for (m1, m2, K, S0, V0) in [(50, 25, 100.0, 100.0, 0.04), (100, 50, 93.0, 100.0, 0.04),
+                                (100, 50, 70.0, 100.0, 0.04 + 1e-6), (20, 10, 120.0, 100.0, 0.09)]:
+        s, ds, v, dv = R.grid(m1, m2, K, S0, V0)
+        grids.append(dict(m1=m1, m2=m2, K=K, S0=S0, V0=V0, s=[repr(float(x)) for x in s],
+                          v=[repr(float(x)) for x in v]))
+    json.dump(grids, open(os.path.join(OUT, "grids.json"), "w"), indent=0)
+
+    # ---- single solves: price, digest of the full U, exercise region (lambda > 0) digest and count
+    solves = []
+    for (m1, m2, N) in [(50, 25, 20), (100, 50, 20), (100, 50, 50), (20, 10, 7), (64, 32, 9)]:
+        for style in (0, 1):
+            for dv in (None, DIVS):
+                for put in (0, 1):
+                    for rf in (0.0, 0.01):
+                        for K in (93.0, 100.0):
+                            if (m1, m2, N) == (100, 50, 50) and (rf != 0.0 or K != 100.0):
+                                continue
+                            if (m1, m2, N) == (64, 32, 9) and (put or rf != 0.0):
+                                continue
+                            b = dict(BASE)
+                            b["r_f"] = rf
+                            r = R.solve_batch([K], N, 1.0 / N, m1=m1, m2=m2, style=style, divs=dv, payoff_put=put,
+                                              want_U=True, want_lambda=True, **b)
+                            lam = r["lambda"][0]
+                            mask = (lam > 0).astype(np.uint8)
+                            solves.append(dict(m1=m1, m2=m2, N=N, T=1.0, style=style, div=dv is not None, put=put,
+                                               r_f=rf, K=K, price=repr(float(r["prices"][0])),
+                                               U_sha256=digest(r["U"][0]),
+                                               lam_sha256=digest(lam) if style else None,
+                                               exercise_count=int(mask.sum()) if style else 0,
+                                               exercise_sha256=hashlib.sha256(mask.tobytes()).hexdigest() if style else None))
+    json.dump(dict(base=BASE, divs=DIVS, cases=solves), open(os.path.join(OUT, "solves.json"), "w"), indent=0)
+
+    # ---- the survey's pinned values re-derived from the reference build
+    named = {}
+    named["EU_call_S_N20"] = R.solve_batch([100.0], 20, 1 / 20, m1=50, m2=25, **BASE)["prices"][0]
+    named["EU_call_M_N20"] = R.solve_batch([100.0], 20, 1 / 20, m1=100, m2=50, **BASE)["prices"][0]
+    named["AMDIV_call_M_N50"] = R.solve_batch([100.0], 50, 1 / 50, m1=100, m2=50, style=1, divs=DIVS, **BASE)["prices"][0]
+    named["AMDIV_put_M_N50"] = R.solve_batch([100.0], 50, 1 / 50, m1=100, m2=50, style=1, divs=DIVS, payoff_put=1, **BASE)["prices"][0]
+    named["CS_shuffled_S_N20"] = R.host_scheme(1, K=100.0, T=1.0, m1=50, m2=25, N=20, **BASE)
+    named["CS_shuffled_M_N20"] = R.host_scheme(1, K=100.0, T=1.0, m1=100, m2=50, N=20, **BASE)
+    named["DO_host_S_N20"] = R.host_scheme(0, K=100.0, T=1.0, m1=50, m2=25, N=20, **BASE)
+    json.dump({k: repr(float(v)) for k, v in named.items()}, open(os.path.join(OUT, "named.json"), "w"), indent=0)
+
+    # ---- Jacobians (src/jacobian_computation.cpp:204-364 and variants)
+    jac = []
+    for (m1, m2, N, style, dv, strikes) in [(25, 20, 20, 0, None, [90.0, 100.0, 107.5]),
+                                           (50, 25, 20, 0, None, [95.0, 100.0]),
+                                           (50, 25, 20, 1, DIVS, [95.0, 105.0]),
+                                           (50, 25, 20, 1, None, [100.0]),
+                                           (50, 25, 20, 0, DIVS, [100.0])]:
+        r = R.solve_batch(strikes, N, 1.0 / N, m1=m1, m2=m2, style=style, divs=dv, jac=1, eps=1e-6, **BASE)
+        jac.append(dict(m1=m1, m2=m2, N=N, style=style, div=dv is not None, strikes=strikes, eps=1e-6,
+                        base=[repr(float(x)) for x in r["prices"]],
+                        J=[[repr(float(x)) for x in row] for row in r["J"]]))
+    # multi-maturity (src/heston_calibration.cpp:2174)
+    Ns = np.array([20, 25, 30], dtype=np.int32)
+    Ts = np.array([1.0, 1.25, 1.5])
+    r = R.solve_batch([95.0, 100.0, 105.0], Ns, Ts / Ns, maturities=Ts, m1=30, m2=15, jac=1, multi=1, **BASE)
+    jac.append(dict(m1=30, m2=15, N=[int(x) for x in Ns], T=[float(x) for x in Ts], style=0, div=False,
+                    strikes=[95.0, 100.0, 105.0], eps=1e-6, multi=1, base=[repr(float(x)) for x in r["prices"]],
+                    J=[[repr(float(x)) for x in row] for row in r["J"]]))
+    json.dump(dict(base=BASE, divs=DIVS, cases=jac), open(os.path.join(OUT, "jacobians.json"), "w"), indent=0)
+
+    # ---- LM update (src/jacobian_computation.cpp:107-195) on a fixed pseudo-random system
+    rng = np.random.default_rng(20261018)
+    Jr = rng.normal(size=(37, 5))
+    rr = rng.normal(size=37)
+    lm = dict(J=[[repr(float(x)) for x in row] for row in Jr], r=[repr(float(x)) for x in rr], cases=[])
+    for lam in (0.01, 1e-7, 10.0):
+        lm["cases"].append(dict(lam=lam, delta=[repr(float(x)) for x in R.lm_update(Jr, rr, lam)]))
+    A = Jr[:5, :].T @ Jr[:5, :] + np.eye(5)
+    b = rr[:5]
+    lm["solve5"] = dict(A=[[repr(float(x)) for x in row] for row in A], b=[repr(float(x)) for x in b],
+                        x=[repr(float(x)) for x in R.solve5(A, b)])
+    json.dump(lm, open(os.path.join(OUT, "lm_update.json"), "w"), indent=0)
+
+    # ---- Black-Scholes helper (src/bs.hpp:44)
+    bs = [dict(S=100.0, K=K, r=0.025, vol=0.2, T=T, price=repr(float(R.bs_call(100.0, K, 0.025, 0.2, T))))
+          for K in (90.0, 95.0, 100.0, 104.5, 110.0) for T in (0.25, 1.0, 2.75)]
+    json.dump(bs, open(os.path.join(OUT, "bs.json"), "w"), indent=0)
+
+    # ---- LM trajectory of the reference's shipped multi-maturity driver set-up
+    # (src/heston_calibration.cpp:2428-2925: 10 maturities x 20 strikes, 51x26 grid).  The loop below is
+    # the same LM loop driven through the reference's compute_jacobian_multi_maturity /
+    # compute_base_prices_multi_maturity / compute_parameter_update_on_device.
+    mats = [1.0 + i * 0.25 if i < 8 else 3.0 + (i - 8) * 0.5 for i in range(10)]
+    strikes = [100.0 * 0.95 + i * 0.5 for i in range(20)]
+    K, T, N = [], [], []
+    for Tm in mats:
+        for s in strikes:
+            K.append(s)
+            T.append(Tm)
+            N.append(max(20, int(Tm * 20)))
+    K, T, N = np.array(K), np.array(T), np.array(N, dtype=np.int32)
+    dt = T / N
+    market = np.array([R.bs_call(100.0, k, 0.025, 0.2, t) for k, t in zip(K, T)])
+    n = K.size
+    tol, dtol = 0.1 * math.sqrt(n), 0.1 * (1.0 + math.log(n))
+    cur = dict(BASE)
+    lam = 0.01
+    traj = []
+    for it in range(15):
+        r = R.solve_batch(K, N, dt, maturities=T, m1=50, m2=25, jac=1, multi=1, **cur)
+        res = market - r["prices"]
+        delta = R.lm_update(r["J"], res, lam)
+        nw = dict(cur)
+        nw["kappa"] = max(1e-3, cur["kappa"] + delta[0])
+        nw["eta"] = max(1e-2, cur["eta"] + delta[1])
+        nw["sigma"] = max(1e-2, cur["sigma"] + delta[2])
+        nw["rho"] = min(1.0, max(-1.0, cur["rho"] + delta[3]))
+        nw["V0"] = max(1e-2, cur["V0"] + delta[4])
+        dn = 0.0
+        for d in delta:
+            dn += d * d
+        dn = math.sqrt(dn)
+        err = 0.0
+        for x in res:
+            err += x * x
+        traj.append(dict(iter=it, lam=lam, err=repr(float(err)), delta_norm=repr(float(dn)),
+                         delta=[repr(float(x)) for x in delta]))
+        if dn < dtol or err < tol:
+            cur = nw
+            break
+        r2 = R.solve_batch(K, N, dt, maturities=T, m1=50, m2=25, multi=1, **nw)
+        nerr = 0.0
+        for x in market - r2["prices"]:
+            nerr += x * x
+        if nerr < err:
+            cur = nw
+            lam = max(lam / 10.0, 1e-7)
+        else:
+            lam = min(lam * 10.0, 1e7)
+    json.dump(dict(n=n, tol=tol, delta_tol=dtol, iterations=len(traj), trajectory=traj,
+                   params=[repr(float(cur[k])) for k in ("kappa", "eta", "sigma", "rho", "V0")],
+                   survey=dict(kappa="4.560782419250094", eta="0.03985674060896215", sigma="0.1047557213238867",
+                               rho="-0.112460685320953", v0="0.04208380263222991", err="1.294560550586723")),
+              open(os.path.join(OUT, "lm_multi_maturity.json"), "w"), indent=0)
+    print("golden fixtures written to", OUT)
+
+
+if __name__ == "__main__":
+    main()

@@ -41,6 +41,8 @@ struct hadi_ctx {
   int sm_count = 0;
   std::string err;
   long long launches = 0;
+  long long exact_reruns = 0;
+  long long h2d_bytes = 0, d2h_bytes = 0;  // cumulative transfer volume (bench.py reports it per step)
   std::vector<DevBuf> pool;  // caching allocator: device and pinned-host blocks are reused across batches
   // s-grids depend only on (m1, K, S0): cache them across calls (an LM run re-prices the same
   // strikes dozens of times; the reference likewise builds its GridViews once, before the loop).
@@ -232,6 +234,13 @@ void hadi_destroy(hadi_ctx* ctx) {
 
 const char* hadi_last_error(const hadi_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
 long long hadi_kernel_launches(const hadi_ctx* ctx) { return ctx ? ctx->launches : 0; }
+long long hadi_exact_reruns(const hadi_ctx* ctx) { return ctx ? ctx->exact_reruns : 0; }
+int hadi_transfer_bytes(const hadi_ctx* ctx, long long* h2d, long long* d2h) {
+  if (!ctx) return HADI_ERR_ARG;
+  if (h2d) *h2d = ctx->h2d_bytes;
+  if (d2h) *d2h = ctx->d2h_bytes;
+  return HADI_OK;
+}
 
 int hadi_grid(int m1, int m2, double K, double S0, double V0, double* s, double* v) {
   if (m1 < 1 || m2 < 1 || !s || !v) return HADI_ERR_ARG;
@@ -451,6 +460,7 @@ int hadi_batch_create(hadi_ctx* ctx, const hadi_model* model, const hadi_numeric
   }
   const size_t o_d = put(dv.data(), sizeof(double) * dv.size());
   cudaError_t e = cudaMemcpyAsync(d_stage, h_stage, off, cudaMemcpyHostToDevice, ctx->stream);
+  ctx->h2d_bytes += (long long)off;
   if (e != cudaSuccess) {
     release_all();
     return cuda_fail(ctx, e, "H2D");
@@ -473,8 +483,8 @@ int hadi_batch_create(hadi_ctx* ctx, const hadi_model* model, const hadi_numeric
   L.out_values = d_values;
   L.out_U = nullptr;
   L.out_lam = nullptr;
-  L.prof = (long long*)take(sizeof(long long) * 8 * (size_t)b->grid_ctas, false);
-  if (L.prof) cudaMemsetAsync(L.prof, 0, sizeof(long long) * 8 * (size_t)b->grid_ctas, ctx->stream);
+  L.prof = (long long*)take(sizeof(long long) * (8 * (size_t)b->grid_ctas + 1), false);
+  if (L.prof) cudaMemsetAsync(L.prof, 0, sizeof(long long) * (8 * (size_t)b->grid_ctas + 1), ctx->stream);
   if (cudaEventCreate(&b->ev0) != cudaSuccess || cudaEventCreate(&b->ev1) != cudaSuccess) {
     release_all();
     return cuda_fail(ctx, cudaGetLastError(), "event");
@@ -510,6 +520,7 @@ int hadi_batch_fetch(hadi_batch* b, double* values) {
   cudaError_t e = cudaMemcpyAsync(b->h_values, b->L.out_values, sizeof(double) * (size_t)std::max(b->n_items, 1),
                                   cudaMemcpyDeviceToHost, ctx->stream);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "D2H");
+  ctx->d2h_bytes += (long long)(sizeof(double) * (size_t)b->n_items);
   e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "kernel execution");
   if (b->n_items > 0) std::memcpy(values, b->h_values, sizeof(double) * (size_t)b->n_items);
@@ -533,10 +544,11 @@ int hadi_batch_phase_cycles(hadi_batch* b, long long* out8) {
   if (!b || !out8 || !b->L.prof) return HADI_ERR_ARG;
   cudaSetDevice(b->ctx->device);
   cudaStreamSynchronize(b->ctx->stream);
-  std::vector<long long> h((size_t)8 * b->grid_ctas);
+  std::vector<long long> h((size_t)8 * b->grid_ctas + 1);
   if (cudaMemcpy(h.data(), b->L.prof, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost) != cudaSuccess)
     return cuda_fail(b->ctx, cudaGetLastError(), "D2H prof");
   for (int k = 0; k < 8; ++k) out8[k] = 0;
+  b->ctx->exact_reruns = h[(size_t)8 * b->grid_ctas];  // items re-solved with IEEE division since batch creation
   for (int c = 0; c < b->grid_ctas; ++c)
     for (int k = 0; k < 8; ++k) out8[k] += h[(size_t)c * 8 + k];
   return HADI_OK;

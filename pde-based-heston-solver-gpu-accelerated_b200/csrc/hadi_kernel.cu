@@ -15,6 +15,7 @@
 // Compile with -fmad=false: parity with the reference requires un-fused multiplies and adds.
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <type_traits>
 
 #include "hadi_launch.h"
@@ -178,8 +179,14 @@ __global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch
     HADI_TICK(0)
     // fast pass; if any guarded division left its range (never observed on option data), the item is
     // re-solved with IEEE divisions so that the published value is exact in every case
-    if (hadi_solve_item<NT, M1, M2, false>(L, it, w, feed, tid, tacc, tlast))
+#ifdef HADI_FORCE_EXACT
+    hadi_solve_item<NT, M1, M2, true>(L, it, w, feed, tid, tacc, tlast);
+#else
+    if (hadi_solve_item<NT, M1, M2, false>(L, it, w, feed, tid, tacc, tlast)) {
+      if (tid == 0 && L.prof != nullptr) atomicAdd((unsigned long long*)&L.prof[(size_t)gridDim.x * 8], 1ULL);
       hadi_solve_item<NT, M1, M2, true>(L, it, w, feed, tid, tacc, tlast);
+    }
+#endif
 
     if (tid == 0) L.out_values[it.out] = w.U[it.idx_v * w.ld + it.idx_s];
     if (L.out_U != nullptr || L.out_lam != nullptr) {
@@ -212,7 +219,8 @@ __global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch
   X(0, 320, 2, 100, 50, true)  \
   X(1, 256, 3, 50, 25, true)   \
   X(2, 416, 2, 0, 0, false)    \
-  X(3, 1024, 1, 0, 0, false)
+  X(3, 1024, 1, 0, 0, false)   \
+  X(4, 320, 2, 100, 50, false)
 
 struct VariantInfo {
   int threads, m1, m2;
@@ -227,7 +235,7 @@ const VariantInfo* variants() {
   };
   return v;
 }
-constexpr int kNumVariants = 4;
+constexpr int kNumVariants = 5;
 
 }  // namespace
 
@@ -240,7 +248,10 @@ int hadi_douglas_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj
   const VariantInfo* v = variants();
   int pick = -1;
   size_t smem = 0;
+  // development aid: HADI_FORCE_VARIANT=<id> restricts the choice (e.g. 2 = run-time dims, direct loads)
+  const char* force = getenv("HADI_FORCE_VARIANT");
   for (int k = 0; k < kNumVariants; ++k) {
+    if (force && atoi(force) != k) continue;
     if (v[k].m1 != 0 && (v[k].m1 != m1 || v[k].m2 != m2)) continue;
     if (v[k].threads < m1 + 1 || v[k].threads - 1 <= m2) continue;
     smem = hadi_smem_layout(m1, m2, ld, n1, n2, pj, v[k].ring).total;

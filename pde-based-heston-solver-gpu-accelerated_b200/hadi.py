@@ -28,7 +28,8 @@ EXPORTS = [
     "hadi_price_batch", "hadi_jacobian_batch", "hadi_batch_create", "hadi_batch_num_items",
     "hadi_batch_launch", "hadi_batch_values_dev", "hadi_batch_fetch", "hadi_batch_elapsed_ms",
     "hadi_batch_destroy", "hadi_jacobian_assemble", "hadi_partition", "hadi_item_costs", "hadi_solve5",
-    "hadi_lm_update", "hadi_calibrate", "hadi_grid", "hadi_bs_call",
+    "hadi_lm_update", "hadi_calibrate", "hadi_grid", "hadi_bs_call", "hadi_transfer_bytes", "hadi_measure_fp64",
+    "hadi_batch_phase_cycles",
 ]
 
 
@@ -115,6 +116,9 @@ def lib():
         L.hadi_grid.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _dp, _dp]
         L.hadi_bs_call.argtypes = [C.c_double] * 5
         L.hadi_bs_call.restype = C.c_double
+        L.hadi_transfer_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+        L.hadi_measure_fp64.argtypes = [C.c_int] + [C.POINTER(C.c_double)] * 3
+        L.hadi_batch_phase_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
         _lib = L
     return _lib
 
@@ -164,6 +168,15 @@ def grid(m1, m2, K, S0, V0):
     if rc != OK:
         raise HadiError(rc)
     return s, v
+
+
+def measure_fp64(device=0):
+    """(un-fused DMUL+DADD TFLOP/s, DFMA TFLOP/s, dependent-DADD latency ns) measured on `device`."""
+    a, b, c = C.c_double(), C.c_double(), C.c_double()
+    rc = lib().hadi_measure_fp64(device, C.byref(a), C.byref(b), C.byref(c))
+    if rc != OK:
+        raise HadiError(rc)
+    return a.value, b.value, c.value
 
 
 def bs_call(S, K, r, vol, T):
@@ -246,6 +259,11 @@ class Context:
     @property
     def kernel_launches(self):
         return lib().hadi_kernel_launches(self._h)
+
+    def transfer_bytes(self):
+        a, b = C.c_longlong(0), C.c_longlong(0)
+        self._check(lib().hadi_transfer_bytes(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def price_batch(self, model, num, pts, n, want_U=False, want_lambda=False):
         P = (num.num.m1 + 1) * (num.num.m2 + 1)

@@ -1,0 +1,65 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed for the (tiny) exchange.
+
+The path shards embarrassingly: work items — options, or option x Jacobian column —
+are independent PDE solves.  Each rank solves a contiguous, cost-balanced slice (hadi_partition) on its
+own GPU; the only exchange is one all-gather of the item values (8 bytes per item).  Every rank then
+assembles J and runs the replicated LM update in the same summation order, so ranks stay bit-identical
+without a broadcast.  There is no data-path collective inside the solver.
+"""
+import ctypes as C
+
+import numpy as np
+
+
+def slices(hadi, costs, world):
+    """[(begin, end)] per rank from the C partitioner."""
+    return [hadi.partition(costs, world, r) for r in range(world)]
+
+
+def allgather_values(mine, counts, dist=None, device=None):
+    """All-gather variable-length float64 slices in rank order (pads to the longest slice)."""
+    import torch
+
+    if dist is None:
+        import torch.distributed as dist
+    world = dist.get_world_size()
+    mx = max(max(counts), 1)
+    buf = torch.zeros(mx, dtype=torch.float64, device=device)
+    if len(mine):
+        buf[:len(mine)] = torch.as_tensor(np.asarray(mine, dtype=np.float64), device=device)
+    out = [torch.zeros(mx, dtype=torch.float64, device=device) for _ in range(world)]
+    dist.all_gather(out, buf)
+    return np.concatenate([out[r][:counts[r]].cpu().numpy() for r in range(world)]) if sum(counts) else np.zeros(0)
+
+
+def solve_items_sharded(hadi, num, pts, n, mode, local_solve, rank, world, device=None, dist=None):
+    """Solve all items of a batch across `world` ranks.  local_solve(begin, end) -> values of that slice
+    (on a GPU rank: a hadi Batch launch + fetch).  Returns every item value, identical on every rank."""
+    costs = hadi.item_costs(num, pts, n, mode)
+    sl = slices(hadi, costs, world)
+    b, e = sl[rank]
+    mine = local_solve(b, e) if e > b else np.zeros(0)
+    if world == 1:
+        return np.asarray(mine, dtype=np.float64)
+    return allgather_values(mine, [x[1] - x[0] for x in sl], dist=dist, device=device)
+
+
+def make_comm(hadi, rank, world, device=None, dist=None):
+    """hadi_comm for hadi_calibrate: the C++ LM driver calls back into torch.distributed for its one
+    all-gather per solver call.  Keep the returned object alive while it is in use."""
+    def _cb(user, mine_p, my_count, all_p, counts_p, displs_p, w):
+        try:
+            counts = [counts_p[r] for r in range(w)]
+            mine = np.ctypeslib.as_array(mine_p, shape=(max(my_count, 1),))[:my_count].copy()
+            full = allgather_values(mine, counts, dist=dist, device=device)
+            total = sum(counts)
+            if total:
+                np.ctypeslib.as_array(all_p, shape=(total,))[:] = full
+            return 0
+        except Exception:  # never let an exception cross the C ABI
+            return 1
+
+    fn = hadi.ALLGATHER_FN(_cb)
+    comm = hadi.Comm(rank, world, fn, None)
+    comm._keep = (fn, _cb)
+    return comm

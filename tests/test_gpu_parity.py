@@ -1,0 +1,267 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (libhadi.so), against the oracle.
+
+Bar (BASELINE.json north_star): 1e-10 relative on prices and Jacobian entries, exact exercise-boundary
+indices.  The implementation is bit-faithful, so the tests demand EQUALITY of every grid value (signed
+zeros aside) — which also makes the Jacobian, a 1e-6 forward difference, exact.
+"""
+import hashlib
+import math
+
+import numpy as np
+import pytest
+
+from conftest import BASE, DIVS, golden
+
+pytestmark = pytest.mark.gpu
+
+
+def digest(a):
+    a = np.ascontiguousarray(a, dtype=np.float64) + 0.0
+    return hashlib.sha256(a.tobytes()).hexdigest()
+
+
+def solve_gpu(hadi, ctx, K, N, T, m1, m2, style=0, put=0, divs=None, model=None, theta=0.8):
+    mdl = hadi.make_model(**(model or BASE))
+    num = hadi.make_numerics(m1, m2, theta, style, put, hadi.DOUGLAS, divs)
+    pts, n = hadi.make_points(K, T, N)
+    return ctx.price_batch(mdl, num, pts, n, want_U=True, want_lambda=True)
+
+
+def test_native_library_is_the_one_running(hadi, ctx):
+    import os
+
+    assert os.path.exists(hadi.LIB_PATH)
+    before = ctx.kernel_launches
+    solve_gpu(hadi, ctx, [100.0], 5, 1.0, 50, 25)
+    assert ctx.kernel_launches == before + 1
+    with open("/proc/self/maps") as f:
+        assert "libhadi.so" in f.read()
+
+
+@pytest.mark.parametrize("m1,m2,N", [(50, 25, 20), (100, 50, 20), (20, 10, 7), (64, 32, 9), (40, 40, 6), (300, 12, 5)])
+def test_single_solves_match_oracle_bitwise(hadi, ctx, oracle, m1, m2, N):
+    """Specialised variants (101x51, 51x26) and the run-time-dimension variants, all four reference
+    functions (European / American x with / without dividends), call and put payoff, r_f = 0 and != 0."""
+    for style in (0, 1):
+        for dv in (None, DIVS):
+            for put in (0, 1):
+                for rf in (0.0, 0.01):
+                    b = dict(BASE)
+                    b["r_f"] = rf
+                    o = oracle.solve(93.0, N, 1.0 / N, m1=m1, m2=m2, theta=0.8, style=style, divs=dv, payoff_put=put,
+                                     **b)
+                    g = solve_gpu(hadi, ctx, [93.0], N, 1.0, m1, m2, style, put, dv, b)
+                    assert g["prices"][0] == o["price"]
+                    assert np.array_equal(g["U"][0], o["U"])
+                    if style:
+                        assert np.array_equal(g["lambda"][0], o["lambda"])
+                        assert np.array_equal(g["lambda"][0] > 0, o["lambda"] > 0)  # exercise region, exact
+
+
+def test_golden_fixtures(hadi, ctx):
+    """Against the committed vectors produced by the reference's own sources."""
+    G = golden("solves.json")
+    for c in G["cases"]:
+        b = dict(G["base"])
+        theta = b.pop("theta")
+        b["r_f"] = c["r_f"]
+        g = solve_gpu(hadi, ctx, [c["K"]], c["N"], c["T"], c["m1"], c["m2"], c["style"], c["put"],
+                      G["divs"] if c["div"] else None, b, theta)
+        assert repr(float(g["prices"][0])) == c["price"], c
+        assert digest(g["U"][0]) == c["U_sha256"], c
+        if c["style"]:
+            mask = (g["lambda"][0] > 0).astype(np.uint8)
+            assert int(mask.sum()) == c["exercise_count"]
+            assert hashlib.sha256(mask.tobytes()).hexdigest() == c["exercise_sha256"]
+    N = golden("named.json")
+    g = solve_gpu(hadi, ctx, [100.0], 50, 1.0, 100, 50, 1, 0, DIVS)
+    assert repr(float(g["prices"][0])) == N["AMDIV_call_M_N50"] == "5.303861863205091"
+    assert int((g["lambda"][0] > 0).sum()) == 233
+    # first exercised s-index on the V0 row (idx_v = 16 at the 101x51 grid)
+    row = g["lambda"][0].reshape(51, 101)[16]
+    assert int(np.argmax(row > 0)) == 1
+
+
+def test_jacobians_match_golden_and_oracle(hadi, ctx, oracle):
+    G = golden("jacobians.json")
+    for c in G["cases"]:
+        b = dict(G["base"])
+        theta = b.pop("theta")
+        mdl = hadi.make_model(**b)
+        num = hadi.make_numerics(c["m1"], c["m2"], theta, c["style"], 0, 0, G["divs"] if c["div"] else None)
+        if c.get("multi"):
+            pts, n = hadi.make_points(c["strikes"], c["T"], c["N"])
+        else:
+            pts, n = hadi.make_points(c["strikes"], 1.0, c["N"])
+        J, base = ctx.jacobian_batch(mdl, num, pts, n, c["eps"])
+        assert [repr(float(x)) for x in base] == c["base"]
+        assert [[repr(float(x)) for x in row] for row in J] == c["J"]
+    # 1e-10 relative would already fail on a single ulp of price noise (eps = 1e-6): check it explicitly
+    Jg, bg = ctx.jacobian_batch(hadi.make_model(**BASE), hadi.make_numerics(50, 25, 0.8), *hadi.make_points([97.0, 103.0], 1.0, 20))
+    Jo, bo = oracle.jacobian_batch([97.0, 103.0], 20, 1 / 20, m1=50, m2=25, theta=0.8, **BASE)
+    assert np.max(np.abs(Jg - Jo) / np.abs(Jo)) <= 1e-10 and np.array_equal(Jg, Jo) and np.array_equal(bg, bo)
+
+
+def test_batch_is_order_independent_and_idempotent(hadi, ctx, oracle):
+    """A 600-option multi-maturity chain (more items than resident CTAs, mixed costs): every option
+    must equal its stand-alone solve, whatever the batch order, and a second launch must reproduce it."""
+    rng = np.random.default_rng(7)
+    K = np.round(rng.uniform(60, 140, size=600), 2)
+    T = rng.choice([0.25, 0.5, 1.0, 2.0], size=600)
+    N = np.maximum(20, (20 * T).astype(int))
+    mdl = hadi.make_model(**BASE)
+    num = hadi.make_numerics(50, 25, 0.8, hadi.AMERICAN, hadi.CALL, 0, DIVS)
+    pts, n = hadi.make_points(K, T, N)
+    a = ctx.price_batch(mdl, num, pts, n)["prices"]
+    bt = ctx.batch(mdl, num, pts, n)
+    bt.launch()
+    b1 = bt.fetch().copy()
+    bt.launch()
+    b2 = bt.fetch().copy()
+    assert np.array_equal(a, b1) and np.array_equal(b1, b2)
+    perm = rng.permutation(600)
+    ptsp, _ = hadi.make_points(K[perm], T[perm], N[perm])
+    c = ctx.price_batch(mdl, num, ptsp, n)["prices"]
+    assert np.array_equal(c, a[perm])
+    for k in rng.choice(600, size=12, replace=False):
+        o = oracle.solve(float(K[k]), int(N[k]), float(T[k]) / int(N[k]), m1=50, m2=25, theta=0.8, style=1, divs=DIVS,
+                         want_U=False, want_lambda=False, **BASE)
+        assert a[k] == o["price"]
+
+
+def test_config2_full_size_properties(hadi, ctx, oracle):
+    """BASELINE config 2 at full size: 500 American options with dividends, 101x51 grid, 50 steps.
+    Size-independent properties + a sample against the oracle."""
+    K = [70 + 0.12 * i for i in range(500)]
+    mdl = hadi.make_model(**BASE)
+    num_am = hadi.make_numerics(100, 50, 0.8, hadi.AMERICAN, hadi.CALL, 0, DIVS)
+    num_eu = hadi.make_numerics(100, 50, 0.8, hadi.EUROPEAN, hadi.CALL, 0, DIVS)
+    pts, n = hadi.make_points(K, 1.0, 50)
+    am = ctx.price_batch(mdl, num_am, pts, n)["prices"]
+    eu = ctx.price_batch(mdl, num_eu, pts, n)["prices"]
+    assert np.all(np.isfinite(am)) and np.all(am > 0)
+    assert np.all(np.diff(am) < 0)                      # call prices fall with the strike
+    assert np.all(am >= eu - 1e-12)                     # early exercise is worth something
+    assert np.all(am >= np.maximum(100.0 - np.array(K), 0.0) - 1e-12)
+    for k in (0, 137, 250, 499):
+        o = oracle.solve(K[k], 50, 1 / 50, m1=100, m2=50, theta=0.8, style=1, divs=DIVS, want_U=False,
+                         want_lambda=False, **BASE)
+        assert am[k] == o["price"]
+    # put payoff under the reference's call boundary vectors
+    num_put = hadi.make_numerics(100, 50, 0.8, hadi.AMERICAN, hadi.PUT, 0, DIVS)
+    pts1, n1 = hadi.make_points([100.0], 1.0, 50)
+    assert repr(float(ctx.price_batch(mdl, num_put, pts1, n1)["prices"][0])) == golden("named.json")["AMDIV_put_M_N50"]
+
+
+def test_global_index_scatter(hadi, ctx):
+    """Results land at CalibrationPoint::global_index (src/heston_calibration.cpp:2165-2171)."""
+    mdl = hadi.make_model(**BASE)
+    num = hadi.make_numerics(50, 25, 0.8)
+    pts, n = hadi.make_points([90.0, 100.0, 110.0], 1.0, 10)
+    straight = ctx.price_batch(mdl, num, pts, n)["prices"].copy()
+    for k, gi in enumerate([2, 0, 1]):
+        pts[k].global_index = gi
+    scattered = ctx.price_batch(mdl, num, pts, n)["prices"]
+    assert scattered[2] == straight[0] and scattered[0] == straight[1] and scattered[1] == straight[2]
+
+
+def test_item_slices_reassemble(hadi, ctx):
+    """Multi-GPU sharding unit: slices of the (option x column) item list solved separately equal the
+    full solve."""
+    mdl = hadi.make_model(**BASE)
+    num = hadi.make_numerics(50, 25, 0.8)
+    pts, n = hadi.make_points([95.0, 100.0, 105.0], [1.0, 1.5, 0.5], [20, 30, 20])
+    full = ctx.batch(mdl, num, pts, n, hadi.MODE_JACOBIAN, 1e-6)
+    full.launch()
+    v = full.fetch().copy()
+    costs = hadi.item_costs(num, pts, n, hadi.MODE_JACOBIAN)
+    parts = []
+    for r in range(4):
+        b, e = hadi.partition(costs, 4, r)
+        bt = ctx.batch(mdl, num, pts, n, hadi.MODE_JACOBIAN, 1e-6, b, e)
+        bt.launch()
+        parts.append(bt.fetch().copy())
+        bt.destroy()
+    assert np.array_equal(np.concatenate(parts), v)
+    J, base = hadi.jacobian_assemble(v, 1e-6)
+    J2, base2 = ctx.jacobian_batch(mdl, num, pts, n, 1e-6)
+    assert np.array_equal(J, J2) and np.array_equal(base, base2)
+
+
+def test_lm_calibration_matches_reference_trajectory(hadi, ctx):
+    """The reference's shipped multi-maturity driver set-up (10 maturities x 20 strikes, 51x26 grid):
+    same iteration count, same error, same final parameters as the reference's own code
+    (tests/golden/lm_multi_maturity.json)."""
+    G = golden("lm_multi_maturity.json")
+    mats = [1.0 + i * 0.25 if i < 8 else 3.0 + (i - 8) * 0.5 for i in range(10)]
+    strikes = [100.0 * 0.95 + i * 0.5 for i in range(20)]
+    K, T, N = [], [], []
+    for Tm in mats:
+        for s in strikes:
+            K.append(s)
+            T.append(Tm)
+            N.append(max(20, int(Tm * 20)))
+    market = [hadi.bs_call(100.0, k, 0.025, 0.2, t) for k, t in zip(K, T)]
+    pts, n = hadi.make_points(K, T, N)
+    res = ctx.calibrate(hadi.make_model(**BASE), hadi.make_numerics(50, 25, 0.8), pts, n, market, 15,
+                        0.1 * math.sqrt(n), 0.1 * (1.0 + math.log(n)))
+    assert res["iterations"] == G["iterations"] == 3 and res["converged"] == 1
+    assert [repr(float(x)) for x in res["params"]] == G["params"]
+    assert repr(float(res["final_error"])) == G["trajectory"][-1]["err"]
+    assert repr(float(res["delta_norm"])) == G["trajectory"][-1]["delta_norm"]
+    assert res["pde_solves"] == 4000
+
+
+def test_lm_american_dividend_small(hadi, ctx, oracle):
+    """American + dividends LM (the reference's second multi-maturity driver family) on a small
+    self-generated surface: identical trajectory to the oracle's LM loop."""
+    K, T, N = [], [], []
+    for Tm in (1.0, 1.5):
+        for s in (95.0, 100.0, 105.0, 110.0):
+            K.append(s)
+            T.append(Tm)
+            N.append(max(20, int(Tm * 20)))
+    gen = dict(BASE, kappa=3.0, eta=0.1, sigma=0.05, rho=0.2, V0=0.06)
+    Na = np.array(N, dtype=np.int32)
+    dts = np.array(T) / Na
+    market = oracle.price_batch(K, Na, dts, m1=30, m2=15, theta=0.8, style=1, divs=DIVS, **gen)
+    n = len(K)
+    kw = dict(max_iter=6, tol=0.03 * math.sqrt(n), delta_tol=0.1 * (1.0 + math.log(n)))
+    o = oracle.calibrate(K, Na, dts, market, m1=30, m2=15, theta=0.8, style=1, divs=DIVS, **kw, **BASE)
+    pts, n = hadi.make_points(K, T, N)
+    g = ctx.calibrate(hadi.make_model(**BASE), hadi.make_numerics(30, 15, 0.8, hadi.AMERICAN, hadi.CALL, 0, DIVS),
+                      pts, n, market, kw["max_iter"], kw["tol"], kw["delta_tol"])
+    assert g["iterations"] == o["iterations"] and g["converged"] == o["converged"]
+    assert g["params"] == o["params"] and g["final_error"] == o["final_error"] and g["lam"] == o["lam"]
+
+
+def test_errors(hadi, ctx):
+    mdl = hadi.make_model(**dict(BASE, S0=100.0))
+    # S0 far outside the s-grid is dropped by the grid construction -> not a node (reference: index_s = -1, UB)
+    num = hadi.make_numerics(50, 25, 0.8)
+    pts, n = hadi.make_points([10.0], 1.0, 10)
+    with pytest.raises(hadi.HadiError) as e:
+        ctx.price_batch(mdl, num, pts, n)
+    assert e.value.code == hadi.ERR_GRID
+    with pytest.raises(hadi.HadiError) as e:
+        ctx.price_batch(mdl, hadi.make_numerics(50, 60, 0.8), *hadi.make_points([100.0], 1.0, 10))
+    assert e.value.code == hadi.ERR_ARG          # m2 > m1
+    with pytest.raises(hadi.HadiError) as e:
+        ctx.price_batch(mdl, hadi.make_numerics(400, 200, 0.8), *hadi.make_points([100.0], 1.0, 10))
+    assert e.value.code == hadi.ERR_SMEM         # 401x201 does not fit the SMEM-resident kernel
+    with pytest.raises(hadi.HadiError) as e:
+        ctx.price_batch(mdl, hadi.make_numerics(50, 25, 0.8, scheme=hadi.CRAIG_SNEYD), *hadi.make_points([100.0], 1.0, 10))
+    assert e.value.code == hadi.ERR_ARG
+    # empty batch is fine
+    pts0, n0 = hadi.make_points([], 1.0, 10)
+    assert ctx.price_batch(mdl, num, pts0, 0)["prices"].size == 0
+
+
+def test_fp64_microbenchmark(hadi):
+    import ctypes as C
+
+    L = hadi.lib()
+    L.hadi_measure_fp64.argtypes = [C.c_int] + [C.POINTER(C.c_double)] * 3
+    a, b, c = C.c_double(), C.c_double(), C.c_double()
+    assert L.hadi_measure_fp64(0, C.byref(a), C.byref(b), C.byref(c)) == 0
+    assert 5.0 < a.value < 60.0 and b.value > a.value and 0.5 < c.value < 50.0
