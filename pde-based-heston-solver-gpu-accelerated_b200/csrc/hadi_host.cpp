@@ -434,6 +434,8 @@ int hadi_batch_create(hadi_ctx* ctx, const hadi_model* model, const hadi_numeric
 
   b->plan = plan;
   b->grid_ctas = std::max(1, std::min(n_items, plan.ctas_per_sm * plan.sm_count));
+  if (const char* cap = getenv("HADI_MAX_CTAS"))  // development aid: cap the persistent grid
+    if (atoi(cap) > 0) b->grid_ctas = std::min(b->grid_ctas, atoi(cap));
   const size_t stride = (hadi_scratch_doubles(m1, m2, g.ld, g.pj) + 31) & ~size_t(31);
   double* d_scratch = (double*)take(sizeof(double) * stride * (size_t)b->grid_ctas, false);
   if (!h_stage || !d_stage || !b->h_values || !d_values || !d_counter || !d_scratch) {
@@ -483,6 +485,8 @@ int hadi_batch_create(hadi_ctx* ctx, const hadi_model* model, const hadi_numeric
   L.out_values = d_values;
   L.out_U = nullptr;
   L.out_lam = nullptr;
+  L.dbg_step = L.dbg_phase = 0;
+  if (const char* ds = getenv("HADI_DEBUG_STOP")) sscanf(ds, "%d:%d", &L.dbg_step, &L.dbg_phase);
   L.prof = (long long*)take(sizeof(long long) * (8 * (size_t)b->grid_ctas + 1), false);
   if (L.prof) cudaMemsetAsync(L.prof, 0, sizeof(long long) * (8 * (size_t)b->grid_ctas + 1), ctx->stream);
   if (cudaEventCreate(&b->ev0) != cudaSuccess || cudaEventCreate(&b->ev1) != cudaSuccess) {
@@ -552,6 +556,17 @@ int hadi_batch_phase_cycles(hadi_batch* b, long long* out8) {
   for (int c = 0; c < b->grid_ctas; ++c)
     for (int k = 0; k < 8; ++k) out8[k] += h[(size_t)c * 8 + k];
   return HADI_OK;
+}
+
+// development aid (not part of include/hadi.h): raw per-CTA debug records, 8 long long per CTA
+int hadi_batch_prof_raw(hadi_batch* b, long long* out, int max_ctas) {
+  if (!b || !out || !b->L.prof) return HADI_ERR_ARG;
+  cudaSetDevice(b->ctx->device);
+  cudaStreamSynchronize(b->ctx->stream);
+  const int n = std::min(max_ctas, b->grid_ctas);
+  if (cudaMemcpy(out, b->L.prof, sizeof(long long) * 8 * (size_t)n, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return cuda_fail(b->ctx, cudaGetLastError(), "D2H prof");
+  return n;
 }
 
 void hadi_batch_destroy(hadi_batch* b) {

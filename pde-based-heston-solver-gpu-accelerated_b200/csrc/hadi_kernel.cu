@@ -27,6 +27,61 @@ namespace {
 #else
 #define HADI_TICK(k)
 #endif
+// development aid: end the item after phase k of step L.dbg_step (state is then dumped by the caller)
+#if defined(HADI_DEBUG_TRACE)
+// development aid: per-step, per-phase position-weighted checksums of U, Y and lambda into out_U
+__device__ __forceinline__ void hadi_dbg_hash(const HadiLaunch& L, const HadiItem& it, const HadiView& w, int n, int k,
+                                              int tid, int nt) {
+  __shared__ unsigned long long hs[3];
+  if (L.out_U == nullptr) return;
+  if (tid < 3) hs[tid] = 0ULL;
+  __syncthreads();
+  unsigned long long a = 0, b = 0, c = 0;
+  for (int p = tid; p < (w.m2 + 1) * (w.m1 + 1); p += nt) {
+    const int j = p / (w.m1 + 1), i = p - j * (w.m1 + 1);
+    const unsigned long long wt = 2ULL * (unsigned long long)p + 1ULL;
+    a += (unsigned long long)__double_as_longlong(w.U[j * w.ld + i]) * wt;
+    b += (unsigned long long)__double_as_longlong(w.Y[j * w.ld + i]) * wt;
+    if (it.style == 1) c += (unsigned long long)__double_as_longlong(hadi_lam_ld(&w.lam[j * w.ld + i])) * wt;
+  }
+  atomicAdd(&hs[0], a); atomicAdd(&hs[1], b); atomicAdd(&hs[2], c);
+  __syncthreads();
+  if (tid < 3) {
+    unsigned long long* tr = reinterpret_cast<unsigned long long*>(L.out_U + (size_t)it.out * w.P + (size_t)(24 * n + 3 * k));
+    tr[tid] = hs[tid];
+  }
+  __syncthreads();
+}
+#define HADI_STOP(k) hadi_dbg_hash(L, it, w, n, k, tid, NT);
+#elif defined(HADI_DEBUG_STOP)
+#define HADI_STOP(k) if (L.dbg_step == n && (L.dbg_phase % 100) == (k)) { stopped = true; break; }
+#else
+#define HADI_STOP(k)
+#endif
+
+#ifdef HADI_DEBUG_LAM
+// development aid: before phase E the multiplier must be identical in Y (shared) and in the global
+// scratch copy; record disagreements in L.prof[blockIdx*8 ..]: count, step, i, j, bits(global),
+// bits(shared), smid, item
+__device__ __forceinline__ void hadi_dbg_check_lam(const HadiLaunch& L, const HadiView& w, int n, int item, int tid, int nt) {
+  const HadiMap mp = hadi_map(w.m1, w.m2, tid, nt);
+  if (!mp.active) return;
+  for (int j = mp.j0; j < mp.j1; ++j) {
+    const double lg = hadi_lam_ld(&w.lam[j * w.ld + mp.i]);
+    const double ls = w.Y[j * w.ld + mp.i];
+    if (__double_as_longlong(lg) != __double_as_longlong(ls)) {
+      long long* rec = L.prof + (size_t)blockIdx.x * 8;
+      if (atomicAdd((unsigned long long*)&rec[0], 1ULL) == 0ULL) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        rec[1] = n; rec[2] = mp.i; rec[3] = j;
+        rec[4] = __double_as_longlong(lg); rec[5] = __double_as_longlong(ls);
+        rec[6] = smid; rec[7] = item;
+      }
+    }
+  }
+}
+#endif
 
 // One item, payoff to price.  Returns (CTA-uniform) whether any guarded division left its fast-path
 // range; EXACT = true compiles every division as IEEE '/'.
@@ -46,7 +101,9 @@ __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiI
   hadi_phase_factor(it, w, vg, tid, NT, NT - 1);
   if constexpr (!std::is_same<Feed, HadiDirectFeed>::value) {
     // the factor streams were written with generic stores and will be read by TMA (async proxy)
+#ifndef HADI_NO_THREADFENCE
     __threadfence();
+#endif
     asm volatile("fence.proxy.async;" ::: "memory");
   }
   __syncthreads();  // the A2 assembly keeps scratch tables in Y: finish it before Y is initialised
@@ -58,7 +115,7 @@ __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiI
       for (int j = mp.j0; j < mp.j1; ++j) {
         w.U[j * w.ld + mp.i] = pay;
         if (it.style == 1) {
-          w.lam[j * w.ld + mp.i] = 0.0;
+          hadi_lam_st(&w.lam[j * w.ld + mp.i], 0.0);
           w.Y[j * w.ld + mp.i] = 0.0;   // phase E reads lambda from Y
         }
       }
@@ -71,45 +128,79 @@ __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiI
   HADI_TICK(0)
 
   int div_cur = 0;
+  bool stopped = false;
   for (int n = 1; n <= it.N; ++n) {
     if (it.nd > 0) {
       const int hit = hadi_dividend_at(n, it.dt, it.nd, L.div_dates, div_cur);
       if (hit >= 0) {  // uniform across the CTA
         hadi_phase_div1(w, L.div_amounts[hit], L.div_pcts[hit], tid, NT);
         __syncthreads();
+        HADI_STOP(1)
         hadi_phase_div2(w, tid, NT);
         __syncthreads();
+        HADI_STOP(2)
         if (it.style == 1) {
           hadi_phase_div3(w, tid, NT);
           __syncthreads();
         }
+        HADI_STOP(3)
       }
     }
     HADI_TICK(0)
+#ifdef HADI_DEBUG_LAM
+    if (it.style == 1) hadi_dbg_check_lam(L, w, n, it.out, tid, NT);
+#endif
     const double e0 = eg[n - 1], e1 = eg[n];
     hadi_phase_explicit<M1, M2>(it, w, e0, e1, tid, NT);
     __syncthreads();
     HADI_TICK(2)
+    HADI_STOP(4)
     hadi_phase_solve_a1<M1, M2, EXACT>(it, w, e0, e1, n, tid, NT, feed, bad, &tacc[1]);
     __syncthreads();
     HADI_TICK(3)
+    HADI_STOP(5)
     hadi_phase_rhs2<M1, M2>(it, w, e0, e1, tid, NT);
     __syncthreads();
     HADI_TICK(7)
+    HADI_STOP(6)
     hadi_phase_solve_a2<M1, M2, EXACT>(it, w, tid, NT, bad);
     __syncthreads();
     HADI_TICK(4)
+    HADI_STOP(7)
     if (it.style == 1) {
       hadi_phase_project<M1, M2, EXACT>(it, w, rdt, tid, NT, bad);
       __syncthreads();
     }
     HADI_TICK(5)
+    HADI_STOP(8)
   }
   if constexpr (!std::is_same<Feed, HadiDirectFeed>::value) {
-    // every chunk issued for this item has been consumed; keep both counters in step on all threads
-    const unsigned nc = (unsigned)(feed.ncf() + feed.ncb());
-    feed.issued = feed.consumed = feed.base = feed.base + (unsigned)it.N * nc;
+#ifdef HADI_DEBUG_STOP
+    if (stopped) {
+      // drain the chunks the producer had in flight so that the ring counters stay consistent
+      __shared__ unsigned s_issued;
+      if (feed.producer(tid)) s_issued = feed.issued;
+      __syncthreads();
+      const unsigned upto = s_issued;
+      if (tid <= m2) {
+        while (feed.consumed != upto) {
+          feed.probe = 0;
+          feed.wait_slot();
+          hadi_mbar_arrive(&feed.empty[feed.consumed % HADI_NS]);
+          feed.consumed++;
+        }
+      }
+      feed.issued = feed.consumed = feed.base = upto;
+      __syncthreads();
+    } else
+#endif
+    {
+      // every chunk issued for this item has been consumed; keep both counters in step on all threads
+      const unsigned nc = (unsigned)(feed.ncf() + feed.ncb());
+      feed.issued = feed.consumed = feed.base = feed.base + (unsigned)it.N * nc;
+    }
   }
+  (void)stopped;
   return __syncthreads_or((int)bad) != 0;
 }
 
@@ -160,6 +251,7 @@ __global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch
     feed.wait_cycles = 0;
 #endif
     feed.probe = 0;
+    feed.zmask = (L.n_items < 0) ? ~0u : 0u;   // a zero the compiler cannot fold (see HadiRingFeed::release)
     if (tid == 0) {
       for (int k = 0; k < HADI_NS; ++k) {
         hadi_mbar_init(&feed.full[k], 1);
@@ -189,12 +281,22 @@ __global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch
 #endif
 
     if (tid == 0) L.out_values[it.out] = w.U[it.idx_v * w.ld + it.idx_s];
+#ifdef HADI_DEBUG_TRACE
+    if (false) {
+#else
     if (L.out_U != nullptr || L.out_lam != nullptr) {
+#endif
       const HadiMap mp = hadi_map(m1, m2, tid, NT);
       if (mp.active) {
         for (int j = mp.j0; j < mp.j1; ++j) {
           const size_t p = (size_t)it.out * w.P + (size_t)j * (m1 + 1) + mp.i;
           if (L.out_U != nullptr) L.out_U[p] = w.U[j * w.ld + mp.i];
+#ifdef HADI_DEBUG_STOP
+          if (L.out_lam != nullptr && L.dbg_step > 0) {
+            L.out_lam[p] = (L.dbg_phase >= 100) ? w.lam[j * w.ld + mp.i] : w.Y[j * w.ld + mp.i];
+            continue;
+          }
+#endif
           if (L.out_lam != nullptr && it.style == 1) L.out_lam[p] = w.lam[j * w.ld + mp.i];
         }
       }

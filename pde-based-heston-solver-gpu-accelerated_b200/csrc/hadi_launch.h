@@ -21,6 +21,7 @@ struct HadiLaunch {
   double* out_U;             // optional [n_items][P] natural layout
   double* out_lam;           // optional [n_items][P]
   long long* prof;           // optional [gridDim.x][8] phase cycle counters (HADI_PHASE_TIMING builds only)
+  int dbg_step, dbg_phase;   // HADI_DEBUG_STOP builds only: end every item after phase dbg_phase of step dbg_step
 };
 
 // Kernel variant chosen for a grid shape (hadi_kernel.cu).
