@@ -9,8 +9,12 @@ pkg = os.path.join(ROOT, "pde-based-heston-solver-gpu-accelerated_b200")
 spec = importlib.util.spec_from_file_location("hadi", os.path.join(pkg, "hadi.py"))
 hadi = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(hadi)
-if os.path.exists(os.path.join(pkg, "libhadi_timing.so")) and "--notiming" not in sys.argv:
+libs = [a for a in sys.argv[1:] if a.endswith(".so")]
+if libs:
+    hadi.LIB_PATH = os.path.join(pkg, libs[0])
+elif os.path.exists(os.path.join(pkg, "libhadi_timing.so")) and "--notiming" not in sys.argv:
     hadi.LIB_PATH = os.path.join(pkg, "libhadi_timing.so")
+print("library:", os.path.basename(hadi.LIB_PATH))
 L = hadi.lib()
 L.hadi_measure_fp64.argtypes = [C.c_int] + [C.POINTER(C.c_double)] * 3
 L.hadi_batch_phase_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
