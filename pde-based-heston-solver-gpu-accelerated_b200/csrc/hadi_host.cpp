@@ -309,7 +309,10 @@ int hadi_batch_create(hadi_ctx* ctx, const hadi_model* model, const hadi_numeric
   *out = nullptr;
   if (!model || !valid_numerics(num) || n < 0 || (n > 0 && !points)) return fail(ctx, HADI_ERR_ARG, "bad argument");
   if (mode != HADI_MODE_PRICE && mode != HADI_MODE_JACOBIAN) return fail(ctx, HADI_ERR_ARG, "bad mode");
-  if (num->scheme != HADI_DOUGLAS) return fail(ctx, HADI_ERR_ARG, "scheme not supported by this kernel");
+  if (num->scheme != HADI_DOUGLAS && num->scheme != HADI_CRAIG_SNEYD) return fail(ctx, HADI_ERR_ARG, "unknown scheme");
+  // the reference defines Craig-Sneyd for European options without dividends only (src/solver.hpp:781)
+  if (num->scheme == HADI_CRAIG_SNEYD && (num->style != HADI_EUROPEAN || num->num_dividends > 0))
+    return fail(ctx, HADI_ERR_ARG, "Craig-Sneyd: European options without dividends only");
   const int nc = n_columns(mode);
   const int total_items = n * nc;
   if (item_end < 0) item_end = total_items;
@@ -321,8 +324,11 @@ int hadi_batch_create(hadi_ctx* ctx, const hadi_model* model, const hadi_numeric
   const int P = (m1 + 1) * (m2 + 1);
   HadiPlan plan;
   {
-    const int prc = hadi_douglas_plan(ctx->device, m1, m2, g.ld, g.n1, g.n2, g.pj, &plan);
-    if (prc < 0) return fail(ctx, HADI_ERR_SMEM, "grid does not fit the shared-memory resident kernel");
+    const bool cs = num->scheme == HADI_CRAIG_SNEYD;
+    int prc = hadi_douglas_plan(ctx->device, m1, m2, g.ld, g.n1, g.n2, g.pj, cs, &plan);
+    // grids beyond shared memory run on the global-state kernel (working set in L2-resident scratch)
+    if (prc < 0 && !cs) prc = hadi_douglas_plan(ctx->device, m1, m2, g.ld, g.n1, g.n2, g.pj, true, &plan);
+    if (prc < 0) return fail(ctx, HADI_ERR_SMEM, "grid too large: m1+1 <= 1024 and the coefficient tables must fit shared memory");
     if (prc > 0) return cuda_fail(ctx, (cudaError_t)prc, "kernel plan");
   }
 
@@ -436,7 +442,7 @@ int hadi_batch_create(hadi_ctx* ctx, const hadi_model* model, const hadi_numeric
   b->grid_ctas = std::max(1, std::min(n_items, plan.ctas_per_sm * plan.sm_count));
   if (const char* cap = getenv("HADI_MAX_CTAS"))  // development aid: cap the persistent grid
     if (atoi(cap) > 0) b->grid_ctas = std::min(b->grid_ctas, atoi(cap));
-  const size_t stride = (hadi_scratch_doubles(m1, m2, g.ld, g.pj) + 31) & ~size_t(31);
+  const size_t stride = hadi_scratch_layout(m1, m2, g.ld, g.pj, plan.global_state, num->scheme == HADI_CRAIG_SNEYD).total;
   double* d_scratch = (double*)take(sizeof(double) * stride * (size_t)b->grid_ctas, false);
   if (!h_stage || !d_stage || !b->h_values || !d_values || !d_counter || !d_scratch) {
     release_all();
@@ -485,6 +491,7 @@ int hadi_batch_create(hadi_ctx* ctx, const hadi_model* model, const hadi_numeric
   L.out_values = d_values;
   L.out_U = nullptr;
   L.out_lam = nullptr;
+  L.scheme = num->scheme;
   L.dbg_step = L.dbg_phase = 0;
   if (const char* ds = getenv("HADI_DEBUG_STOP")) sscanf(ds, "%d:%d", &L.dbg_step, &L.dbg_phase);
   L.prof = (long long*)take(sizeof(long long) * (8 * (size_t)b->grid_ctas + 1), false);

@@ -19,6 +19,7 @@
 #include <type_traits>
 
 #include "hadi_launch.h"
+#include "hadi_phases_cs.cuh"
 
 namespace {
 
@@ -204,7 +205,63 @@ __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiI
   return __syncthreads_or((int)bad) != 0;
 }
 
-template <int NT, int MINB, int M1, int M2, bool RING>
+// Craig-Sneyd (European, no dividends) on the global-state working set: src/solver.hpp:781-907.
+template <int NT, bool EXACT, class Feed>
+__device__ __forceinline__ bool hadi_solve_item_cs(const HadiLaunch& L, const HadiItem& it, HadiView& w,
+                                                   const HadiCsView& cs, Feed& feed, int tid) {
+  const int m1 = L.m1, m2 = L.m2;
+  const double* sg = L.s_pool + it.s_off;
+  const double* vg = L.v_pool + it.v_off;
+  const double* eg = L.e_pool + it.e_off;
+  w.c = it.theta * it.dt;
+  unsigned bad = 0;
+  hadi_phase_tables(it, w, sg, vg, tid, NT);
+  __syncthreads();
+  hadi_phase_factor(it, w, vg, tid, NT, NT - 1);
+  if constexpr (!std::is_same<Feed, HadiDirectFeed>::value) {
+    __threadfence();
+    asm volatile("fence.proxy.async;" ::: "memory");
+  }
+  __syncthreads();
+  {
+    const HadiMap mp = hadi_map(m1, m2, tid, NT);
+    if (mp.active) {
+      const double pay = hadi_ti(w, TI_PAY)[mp.i];
+      for (int j = mp.j0; j < mp.j1; ++j) w.U[j * w.ld + mp.i] = pay;
+    }
+  }
+  __syncthreads();
+  // two A1 solves per step: the feed sees 2N "steps"
+  if constexpr (!std::is_same<Feed, HadiDirectFeed>::value) {
+    if (feed.producer(tid)) feed.produce(0, 2 * it.N, 0);
+  }
+  for (int n = 1; n <= it.N; ++n) {
+    const double e0 = eg[n - 1], e1 = eg[n];
+    hadi_cs_predict(it, w, cs, e0, e1, tid, NT);
+    __syncthreads();
+    hadi_phase_solve_a1<0, 0, EXACT>(it, w, e0, e1, 2 * n - 1, tid, NT, feed, bad, nullptr, 2 * it.N);
+    __syncthreads();
+    hadi_cs_rhs2(it, w, cs, e0, e1, tid, NT);
+    __syncthreads();
+    hadi_phase_solve_a2<0, 0, EXACT>(it, w, tid, NT, bad);   // Y2 -> U
+    __syncthreads();
+    hadi_cs_correct(it, w, cs, e0, e1, tid, NT);
+    __syncthreads();
+    hadi_phase_solve_a1<0, 0, EXACT>(it, w, e0, e1, 2 * n, tid, NT, feed, bad, nullptr, 2 * it.N);
+    __syncthreads();
+    hadi_cs_rhs2(it, w, cs, e0, e1, tid, NT);
+    __syncthreads();
+    hadi_phase_solve_a2<0, 0, EXACT>(it, w, tid, NT, bad);
+    __syncthreads();
+  }
+  if constexpr (!std::is_same<Feed, HadiDirectFeed>::value) {
+    const unsigned nc = (unsigned)(feed.ncf() + feed.ncb());
+    feed.issued = feed.consumed = feed.base = feed.base + (unsigned)(2 * it.N) * nc;
+  }
+  return __syncthreads_or((int)bad) != 0;
+}
+
+template <int NT, int MINB, int M1, int M2, bool RING, bool GLOBAL = false>
 __global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch L) {
   extern __shared__ double smem[];
   __shared__ int s_item;
@@ -219,18 +276,22 @@ __global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch
   HadiView w;
   w.m1 = m1; w.m2 = m2; w.P = (m1 + 1) * (m2 + 1);
   w.ld = hadi_geo_ld(m1); w.n1 = hadi_geo_n1(m1); w.n2 = hadi_geo_n2(m2); w.pj = hadi_geo_pj(m2);
-  const HadiSmemLayout lay = hadi_smem_layout(m1, m2, w.ld, w.n1, w.n2, w.pj, RING);
+  const HadiSmemLayout lay = hadi_smem_layout(m1, m2, w.ld, w.n1, w.n2, w.pj, RING, GLOBAL);
   char* sbase = reinterpret_cast<char*>(smem);
-  double* Ualloc = reinterpret_cast<double*>(sbase + lay.U);
+  double* scratch = L.scratch + (size_t)blockIdx.x * L.scratch_stride;
+  const HadiScratchLayout gl = hadi_scratch_layout(m1, m2, w.ld, w.pj, GLOBAL, GLOBAL && L.scheme == 1);
+  // the working set: shared memory, or (GLOBAL) L2-resident global scratch for grids beyond it
+  double* Ualloc = GLOBAL ? scratch + gl.U : reinterpret_cast<double*>(sbase + lay.U);
   w.U = Ualloc + HADI_HALO * w.ld + 1;
-  w.Y = reinterpret_cast<double*>(sbase + lay.Y);
+  w.Y = GLOBAL ? scratch + gl.Y : reinterpret_cast<double*>(sbase + lay.Y);
   w.ti = reinterpret_cast<double*>(sbase + lay.ti);
   w.tj = reinterpret_cast<double*>(sbase + lay.tj);
   w.divk = reinterpret_cast<int*>(sbase + lay.divk);
-  double* scratch = L.scratch + (size_t)blockIdx.x * L.scratch_stride;
-  w.fM = scratch;
-  w.fB = w.fM + (size_t)m1 * w.pj;
-  w.lam = w.fB + (size_t)m1 * 2 * w.pj;
+  w.fM = scratch + gl.fM;
+  w.fB = scratch + gl.fB;
+  w.lam = scratch + gl.lam;
+  HadiCsView cs;
+  cs.Y0 = scratch + gl.Y0; cs.R0 = scratch + gl.R0; cs.R1 = scratch + gl.R1; cs.R2 = scratch + gl.R2;
   // zero the halo of U once (payoff initialisation and the sweeps only ever write rows 0..m2)
   for (int k = tid; k < (m2 + 1 + 2 * HADI_HALO) * w.ld + 2; k += NT) Ualloc[k] = 0.0;
 
@@ -271,14 +332,23 @@ __global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch
     HADI_TICK(0)
     // fast pass; if any guarded division left its range (never observed on option data), the item is
     // re-solved with IEEE divisions so that the published value is exact in every case
-#ifdef HADI_FORCE_EXACT
-    hadi_solve_item<NT, M1, M2, true>(L, it, w, feed, tid, tacc, tlast);
-#else
-    if (hadi_solve_item<NT, M1, M2, false>(L, it, w, feed, tid, tacc, tlast)) {
-      if (tid == 0 && L.prof != nullptr) atomicAdd((unsigned long long*)&L.prof[(size_t)gridDim.x * 8], 1ULL);
-      hadi_solve_item<NT, M1, M2, true>(L, it, w, feed, tid, tacc, tlast);
+    bool cs_done = false;
+    if constexpr (GLOBAL) {
+      if (L.scheme == 1) {
+        if (hadi_solve_item_cs<NT, false>(L, it, w, cs, feed, tid)) hadi_solve_item_cs<NT, true>(L, it, w, cs, feed, tid);
+        cs_done = true;
+      }
     }
+    if (!cs_done) {
+#ifdef HADI_FORCE_EXACT
+      hadi_solve_item<NT, M1, M2, true>(L, it, w, feed, tid, tacc, tlast);
+#else
+      if (hadi_solve_item<NT, M1, M2, false>(L, it, w, feed, tid, tacc, tlast)) {
+        if (tid == 0 && L.prof != nullptr) atomicAdd((unsigned long long*)&L.prof[(size_t)gridDim.x * 8], 1ULL);
+        hadi_solve_item<NT, M1, M2, true>(L, it, w, feed, tid, tacc, tlast);
+      }
 #endif
+    }
 
     if (tid == 0) L.out_values[it.out] = w.U[it.idx_v * w.ld + it.idx_s];
 #ifdef HADI_DEBUG_TRACE
@@ -317,31 +387,34 @@ __global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch
 // 1:  51 x 26 nodes (the reference's own test / benchmark grid): 256 threads = 5 x 51 (+1), 3 CTAs/SM
 // 2: any grid with m1+1 <= 416 that fits shared memory, run-time dimensions, direct factor loads
 // 3: any grid with m1+1 <= 1024 that fits shared memory, run-time dimensions, one CTA per SM
-#define HADI_VARIANTS(X)        \
-  X(0, 320, 2, 100, 50, true)  \
-  X(1, 256, 3, 50, 25, true)   \
-  X(2, 416, 2, 0, 0, false)    \
-  X(3, 1024, 1, 0, 0, false)   \
-  X(4, 320, 2, 100, 50, false)
+// 5: any grid with m1+1 <= 1024: U and Y in L2-resident global scratch, tables in shared memory, TMA ring for
+//    the A1 factors, one CTA per SM (grids beyond shared memory, e.g. 401 x 201; all Craig-Sneyd solves)
+#define HADI_VARIANTS(X)               \
+  X(0, 320, 2, 100, 50, true, false)  \
+  X(1, 256, 3, 50, 25, true, false)   \
+  X(2, 416, 2, 0, 0, false, false)    \
+  X(3, 1024, 1, 0, 0, false, false)   \
+  X(4, 320, 2, 100, 50, false, false) \
+  X(5, 1024, 1, 0, 0, true, true)
 
 struct VariantInfo {
   int threads, m1, m2;
-  bool ring;
+  bool ring, global_state;
   const void* fn;
 };
 const VariantInfo* variants() {
   static const VariantInfo v[] = {
-#define X(id, nt, minb, a, b, r) {nt, a, b, r, (const void*)hadi_douglas_kernel<nt, minb, a, b, r>},
+#define X(id, nt, minb, a, b, r, g) {nt, a, b, r, g, (const void*)hadi_douglas_kernel<nt, minb, a, b, r, g>},
       HADI_VARIANTS(X)
 #undef X
   };
   return v;
 }
-constexpr int kNumVariants = 5;
+constexpr int kNumVariants = 6;
 
 }  // namespace
 
-int hadi_douglas_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj, HadiPlan* plan) {
+int hadi_douglas_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj, bool need_global, HadiPlan* plan) {
   int max_smem = 0, sms = 0;
   cudaError_t e = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   if (e != cudaSuccess) return (int)e;
@@ -354,9 +427,11 @@ int hadi_douglas_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj
   const char* force = getenv("HADI_FORCE_VARIANT");
   for (int k = 0; k < kNumVariants; ++k) {
     if (force && atoi(force) != k) continue;
+    if (need_global && !v[k].global_state) continue;
     if (v[k].m1 != 0 && (v[k].m1 != m1 || v[k].m2 != m2)) continue;
     if (v[k].threads < m1 + 1 || v[k].threads - 1 <= m2) continue;
-    smem = hadi_smem_layout(m1, m2, ld, n1, n2, pj, v[k].ring).total;
+    if (v[k].ring && v[k].threads <= 32 * ((m2 + 1 + 31) / 32)) continue;   // needs a producer thread past the solver warps
+    smem = hadi_smem_layout(m1, m2, ld, n1, n2, pj, v[k].ring, v[k].global_state).total;
     if (smem > (size_t)max_smem) continue;
     pick = k;
     break;
@@ -368,6 +443,7 @@ int hadi_douglas_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v[pick].fn, v[pick].threads, smem);
   if (e != cudaSuccess) return (int)e;
   if (occ < 1) return -1;
+  plan->global_state = v[pick].global_state;
   plan->variant = pick;
   plan->threads = v[pick].threads;
   plan->ctas_per_sm = occ;
@@ -379,9 +455,9 @@ int hadi_douglas_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj
 int hadi_launch_douglas(const HadiLaunch& L, const HadiPlan& plan, int grid_ctas, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   switch (plan.variant) {
-#define X(id, nt, minb, a, b, r) \
-  case id:                       \
-    hadi_douglas_kernel<nt, minb, a, b, r><<<grid_ctas, nt, plan.smem_bytes, st>>>(L); \
+#define X(id, nt, minb, a, b, r, g) \
+  case id:                          \
+    hadi_douglas_kernel<nt, minb, a, b, r, g><<<grid_ctas, nt, plan.smem_bytes, st>>>(L); \
     break;
     HADI_VARIANTS(X)
 #undef X

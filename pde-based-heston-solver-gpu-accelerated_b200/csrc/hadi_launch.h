@@ -22,10 +22,12 @@ struct HadiLaunch {
   double* out_lam;           // optional [n_items][P]
   long long* prof;           // optional [gridDim.x][8] phase cycle counters (HADI_PHASE_TIMING builds only)
   int dbg_step, dbg_phase;   // HADI_DEBUG_STOP builds only: end every item after phase dbg_phase of step dbg_step
+  int scheme;                // 0 Douglas, 1 Craig-Sneyd (global-state kernel only)
 };
 
 // Kernel variant chosen for a grid shape (hadi_kernel.cu).
 struct HadiPlan {
+  bool global_state;  // U and Y live in L2-resident global scratch (grids beyond shared memory, Craig-Sneyd)
   int variant;        // index of the template instantiation
   int threads;        // CTA size
   int ctas_per_sm;    // resident CTAs per SM at this shared-memory footprint
@@ -37,13 +39,14 @@ struct HadiPlan {
 struct HadiSmemLayout {
   size_t U, Y, ti, tj, divk, ring, bars, total;
 };
-HADI_HD HadiSmemLayout hadi_smem_layout(int m1, int m2, int ld, int n1, int n2, int pj, bool ring) {
+HADI_HD HadiSmemLayout hadi_smem_layout(int m1, int m2, int ld, int n1, int n2, int pj, bool ring,
+                                        bool global_state = false) {
   (void)m1;
   HadiSmemLayout s;
   size_t off = 0;
   // U carries HADI_HALO zero rows above and below and one spare word at either end
-  s.U = off; off += sizeof(double) * ((size_t)(m2 + 1 + 2 * HADI_HALO) * ld + 2);
-  s.Y = off; off += sizeof(double) * (size_t)(m2 + 1) * ld;
+  s.U = off; if (!global_state) off += sizeof(double) * ((size_t)(m2 + 1 + 2 * HADI_HALO) * ld + 2);
+  s.Y = off; if (!global_state) off += sizeof(double) * (size_t)(m2 + 1) * ld;
   s.ti = off; off += sizeof(double) * (size_t)TI_COUNT * n1;
   s.tj = off; off += sizeof(double) * (size_t)TJ_COUNT * n2;
   s.divk = off; off += sizeof(int) * (size_t)n1;
@@ -55,11 +58,28 @@ HADI_HD HadiSmemLayout hadi_smem_layout(int m1, int m2, int ld, int n1, int n2, 
   s.total = off + 16;
   return s;
 }
-// per-CTA global scratch: fM [m1][pj], fB [m1][2*pj], lambda [m2+1][ld]
-inline size_t hadi_scratch_doubles(int m1, int m2, int ld, int pj) {
-  return (size_t)3 * (size_t)m1 * (size_t)pj + (size_t)(m2 + 1) * (size_t)ld;
+// per-CTA global scratch: fM [m1][pj], fB [m1][2*pj], lambda [m2+1][ld]; the global-state kernel adds
+// U (with halo) and Y, and for Craig-Sneyd Y0, R0, R1, R2 — every array starts on a 128-byte boundary
+struct HadiScratchLayout {
+  size_t fM, fB, lam, U, Y, Y0, R0, R1, R2, total;   // offsets in doubles
+};
+HADI_HD HadiScratchLayout hadi_scratch_layout(int m1, int m2, int ld, int pj, bool global_state, bool cs) {
+  HadiScratchLayout s;
+  size_t off = 0;
+  const size_t arr = (size_t)(m2 + 1) * (size_t)ld;
+  s.fM = off; off += (size_t)m1 * pj; off = (off + 15) & ~size_t(15);
+  s.fB = off; off += (size_t)2 * m1 * pj; off = (off + 15) & ~size_t(15);
+  s.lam = off; off += arr; off = (off + 15) & ~size_t(15);
+  s.U = off; if (global_state) off += (size_t)(m2 + 1 + 2 * HADI_HALO) * ld + 2; off = (off + 15) & ~size_t(15);
+  s.Y = off; if (global_state) off += arr; off = (off + 15) & ~size_t(15);
+  s.Y0 = off; if (cs) off += arr; off = (off + 15) & ~size_t(15);
+  s.R0 = off; if (cs) off += arr; off = (off + 15) & ~size_t(15);
+  s.R1 = off; if (cs) off += arr; off = (off + 15) & ~size_t(15);
+  s.R2 = off; if (cs) off += arr; off = (off + 15) & ~size_t(15);
+  s.total = (off + 31) & ~size_t(31);
+  return s;
 }
 
 // defined in hadi_kernel.cu; return 0 or a cudaError_t
-int hadi_douglas_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj, HadiPlan* plan);
+int hadi_douglas_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj, bool need_global, HadiPlan* plan);
 int hadi_launch_douglas(const HadiLaunch& L, const HadiPlan& plan, int grid_ctas, void* stream);

@@ -20,7 +20,8 @@ class Item(C.Structure):
 
 def build():
     so = os.path.join(_HERE, "libhadi_emu.so")
-    srcs = [os.path.join(_HERE, "hadi_emu.cpp"), os.path.join(_CSRC, "hadi_phases.cuh")]
+    srcs = [os.path.join(_HERE, "hadi_emu.cpp"), os.path.join(_CSRC, "hadi_phases.cuh"),
+            os.path.join(_CSRC, "hadi_phases_cs.cuh")]
     if (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
         subprocess.check_call([cxx, "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I" + _CSRC,
@@ -29,7 +30,7 @@ def build():
 
 
 def emu_solve(hadi, K, N, dt, *, S0, V0, r_d, r_f, rho, sigma, kappa, eta, m1, m2, theta, style=0, payoff_put=0,
-              divs=None, nt=384, V0_grid=None):
+              divs=None, nt=384, V0_grid=None, scheme=0):
     """Run one solve through the emulated kernel.  `hadi` is the product's python binding (for hadi_grid)."""
     L = C.CDLL(build())
     assert L.hadi_emu_item_size() == C.sizeof(Item)
@@ -51,7 +52,10 @@ def emu_solve(hadi, K, N, dt, *, S0, V0, r_d, r_f, rho, sigma, kappa, eta, m1, m
     U, lam = np.zeros(P), np.zeros(P)
     price = C.c_double(0.0)
     f = lambda a: a.ctypes.data_as(_dp)
-    rc = L.hadi_emu_solve(C.byref(it), m1, m2, nt, f(s), f(v), f(E), nd, f(dd), f(da), f(dpc), C.byref(price), f(U),
-                          f(lam))
+    if scheme == 1:
+        rc = L.hadi_emu_solve_cs(C.byref(it), m1, m2, nt, f(s), f(v), f(E), C.byref(price), f(U))
+    else:
+        rc = L.hadi_emu_solve(C.byref(it), m1, m2, nt, f(s), f(v), f(E), nd, f(dd), f(da), f(dpc), C.byref(price),
+                              f(U), f(lam))
     assert rc == 0
     return {"price": price.value, "U": U, "lambda": lam}

@@ -247,11 +247,11 @@ def test_errors(hadi, ctx):
         ctx.price_batch(mdl, hadi.make_numerics(50, 60, 0.8), *hadi.make_points([100.0], 1.0, 10))
     assert e.value.code == hadi.ERR_ARG          # m2 > m1
     with pytest.raises(hadi.HadiError) as e:
-        ctx.price_batch(mdl, hadi.make_numerics(400, 200, 0.8), *hadi.make_points([100.0], 1.0, 10))
-    assert e.value.code == hadi.ERR_SMEM         # 401x201 does not fit the SMEM-resident kernel
+        ctx.price_batch(mdl, hadi.make_numerics(2000, 200, 0.8), *hadi.make_points([100.0], 1.0, 10))
+    assert e.value.code == hadi.ERR_SMEM         # more than 1024 s-nodes: no kernel variant
     with pytest.raises(hadi.HadiError) as e:
-        ctx.price_batch(mdl, hadi.make_numerics(50, 25, 0.8, scheme=hadi.CRAIG_SNEYD), *hadi.make_points([100.0], 1.0, 10))
-    assert e.value.code == hadi.ERR_ARG
+        ctx.price_batch(mdl, hadi.make_numerics(50, 25, 0.8, scheme=7), *hadi.make_points([100.0], 1.0, 10))
+    assert e.value.code == hadi.ERR_ARG          # unknown scheme
     # empty batch is fine
     pts0, n0 = hadi.make_points([], 1.0, 10)
     assert ctx.price_batch(mdl, num, pts0, 0)["prices"].size == 0
@@ -265,3 +265,66 @@ def test_fp64_microbenchmark(hadi):
     a, b, c = C.c_double(), C.c_double(), C.c_double()
     assert L.hadi_measure_fp64(0, C.byref(a), C.byref(b), C.byref(c)) == 0
     assert 5.0 < a.value < 60.0 and b.value > a.value and 0.5 < c.value < 50.0
+
+
+# ---- Craig-Sneyd and grids beyond shared memory (global-state kernel) --------------------------------------
+
+def solve_gpu_cs(hadi, ctx, K, N, T, m1, m2, put=0, model=None, theta=0.8):
+    mdl = hadi.make_model(**(model or BASE))
+    num = hadi.make_numerics(m1, m2, theta, hadi.EUROPEAN, put, hadi.CRAIG_SNEYD, None)
+    pts, n = hadi.make_points(K, T, N)
+    return ctx.price_batch(mdl, num, pts, n, want_U=True)
+
+
+def test_craig_sneyd_matches_reference_golden_and_oracle(hadi, ctx, oracle):
+    """CS_scheme_shuffled (src/solver.hpp:781-907): golden prices produced by the reference's own host
+    solver (tests/golden/named.json), full grids against the oracle."""
+    named = golden("named.json")
+    g = solve_gpu_cs(hadi, ctx, [100.0], 20, 1.0, 50, 25)
+    assert g["prices"][0] == float(named["CS_shuffled_S_N20"])
+    g = solve_gpu_cs(hadi, ctx, [100.0], 20, 1.0, 100, 50)
+    assert g["prices"][0] == float(named["CS_shuffled_M_N20"])
+    for (m1, m2, N, K) in ((50, 25, 20, 93.0), (100, 50, 7, 104.0), (36, 18, 5, 100.0)):
+        for put in (0, 1):
+            b = dict(BASE)
+            b["r_f"] = 0.01 if put else 0.0
+            o = oracle.solve(K, N, 1.0 / N, m1=m1, m2=m2, theta=0.8, scheme=1, payoff_put=put, want_lambda=False, **b)
+            g = solve_gpu_cs(hadi, ctx, [K, K + 1.0], N, 1.0, m1, m2, put=put, model=b)
+            assert g["prices"][0] == o["price"]
+            assert np.array_equal(g["U"][0], o["U"])
+
+
+def test_craig_sneyd_rejects_unsupported_combinations(hadi, ctx):
+    mdl = hadi.make_model(**BASE)
+    pts, n = hadi.make_points([100.0], 1.0, 5)
+    for num in (hadi.make_numerics(50, 25, 0.8, hadi.AMERICAN, hadi.CALL, hadi.CRAIG_SNEYD, None),
+                hadi.make_numerics(50, 25, 0.8, hadi.EUROPEAN, hadi.CALL, hadi.CRAIG_SNEYD, DIVS)):
+        with pytest.raises(hadi.HadiError) as e:
+            ctx.price_batch(mdl, num, pts, n)
+        assert e.value.code == hadi.ERR_ARG
+
+
+def test_large_grid_beyond_shared_memory(hadi, ctx, oracle):
+    """BASELINE config 4 shape, 401 x 201 nodes (645 KB per array): U and Y live in L2-resident global
+    scratch.  Few steps against the oracle on the full grid, Douglas (European and American+dividends)
+    and Craig-Sneyd."""
+    m1, m2, N = 400, 200, 3
+    o = oracle.solve(100.0, N, 1.0 / 200, m1=m1, m2=m2, theta=0.8, want_lambda=False, **BASE)
+    g = solve_gpu(hadi, ctx, [100.0, 90.0], N, N / 200.0, m1, m2)
+    assert g["prices"][0] == o["price"] and np.array_equal(g["U"][0], o["U"])
+    o = oracle.solve(100.0, N, 0.21 / N, m1=m1, m2=m2, theta=0.8, style=1, divs=DIVS, **BASE)
+    g = solve_gpu(hadi, ctx, [100.0], N, 0.21, m1, m2, style=1, divs=DIVS)
+    assert g["prices"][0] == o["price"] and np.array_equal(g["U"][0], o["U"])
+    assert np.array_equal(g["lambda"][0] > 0, o["lambda"] > 0)
+    o = oracle.solve(100.0, N, 1.0 / 200, m1=m1, m2=m2, theta=0.8, scheme=1, want_lambda=False, **BASE)
+    g = solve_gpu_cs(hadi, ctx, [100.0], N, N / 200.0, m1, m2)
+    assert g["prices"][0] == o["price"] and np.array_equal(g["U"][0], o["U"])
+
+
+def test_config4_full_size_golden(hadi, ctx):
+    """BASELINE config 4 at full size: European call, 400 x 200 x 200.  Golden prices from the reference's
+    own code (SURVEY.md 8(c) probe): Craig-Sneyd host solver and device Douglas path."""
+    g = solve_gpu_cs(hadi, ctx, [100.0] * 4, 200, 1.0, 400, 200)
+    assert np.all(g["prices"] == 8.8920027296371611)
+    g = solve_gpu(hadi, ctx, [100.0], 200, 1.0, 400, 200)
+    assert g["prices"][0] == 8.8925021574843157
