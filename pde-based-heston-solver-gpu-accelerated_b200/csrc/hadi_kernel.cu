@@ -100,7 +100,7 @@ __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiI
   hadi_phase_tables(it, w, sg, vg, tid, NT);
   __syncthreads();
   hadi_phase_factor(it, w, vg, tid, NT, NT - 1);
-  if constexpr (!std::is_same<Feed, HadiDirectFeed>::value) {
+  if constexpr (Feed::kTma) {
     // the factor streams were written with generic stores and will be read by TMA (async proxy)
 #ifndef HADI_NO_THREADFENCE
     __threadfence();
@@ -123,9 +123,10 @@ __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiI
     }
   }
   __syncthreads();
-  if constexpr (!std::is_same<Feed, HadiDirectFeed>::value) {
+  if constexpr (Feed::kTma) {
     if (feed.producer(tid)) feed.produce(0, it.N, 0);  // first chunks are in flight before step 1
   }
+  if (tid <= m2) feed.begin_item(it.N, tid);
   HADI_TICK(0)
 
   int div_cur = 0;
@@ -169,13 +170,15 @@ __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiI
     HADI_TICK(4)
     HADI_STOP(7)
     if (it.style == 1) {
-      hadi_phase_project<M1, M2, EXACT>(it, w, rdt, tid, NT, bad);
+      // all multiplier loads of a thread's rows are issued before the first is used (one L2 round trip)
+      constexpr int CHP = (M1 == 100 && M2 == 50 && NT / 101 == 3) ? 17 : HADI_CHP;
+      hadi_phase_project<M1, M2, EXACT, CHP>(it, w, rdt, tid, NT, bad);
       __syncthreads();
     }
     HADI_TICK(5)
     HADI_STOP(8)
   }
-  if constexpr (!std::is_same<Feed, HadiDirectFeed>::value) {
+  if constexpr (Feed::kTma) {
 #ifdef HADI_DEBUG_STOP
     if (stopped) {
       // drain the chunks the producer had in flight so that the ring counters stay consistent
@@ -218,7 +221,7 @@ __device__ __forceinline__ bool hadi_solve_item_cs(const HadiLaunch& L, const Ha
   hadi_phase_tables(it, w, sg, vg, tid, NT);
   __syncthreads();
   hadi_phase_factor(it, w, vg, tid, NT, NT - 1);
-  if constexpr (!std::is_same<Feed, HadiDirectFeed>::value) {
+  if constexpr (Feed::kTma) {
     __threadfence();
     asm volatile("fence.proxy.async;" ::: "memory");
   }
@@ -232,9 +235,10 @@ __device__ __forceinline__ bool hadi_solve_item_cs(const HadiLaunch& L, const Ha
   }
   __syncthreads();
   // two A1 solves per step: the feed sees 2N "steps"
-  if constexpr (!std::is_same<Feed, HadiDirectFeed>::value) {
+  if constexpr (Feed::kTma) {
     if (feed.producer(tid)) feed.produce(0, 2 * it.N, 0);
   }
+  if (tid <= m2) feed.begin_item(2 * it.N, tid);
   for (int n = 1; n <= it.N; ++n) {
     const double e0 = eg[n - 1], e1 = eg[n];
     hadi_cs_predict(it, w, cs, e0, e1, tid, NT);
@@ -254,14 +258,14 @@ __device__ __forceinline__ bool hadi_solve_item_cs(const HadiLaunch& L, const Ha
     hadi_phase_solve_a2<0, 0, EXACT>(it, w, tid, NT, bad);
     __syncthreads();
   }
-  if constexpr (!std::is_same<Feed, HadiDirectFeed>::value) {
+  if constexpr (Feed::kTma) {
     const unsigned nc = (unsigned)(feed.ncf() + feed.ncb());
     feed.issued = feed.consumed = feed.base = feed.base + (unsigned)(2 * it.N) * nc;
   }
   return __syncthreads_or((int)bad) != 0;
 }
 
-template <int NT, int MINB, int M1, int M2, bool RING, bool GLOBAL = false>
+template <int NT, int MINB, int M1, int M2, int FEED, bool GLOBAL = false>
 __global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch L) {
   extern __shared__ double smem[];
   __shared__ int s_item;
@@ -276,7 +280,7 @@ __global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch
   HadiView w;
   w.m1 = m1; w.m2 = m2; w.P = (m1 + 1) * (m2 + 1);
   w.ld = hadi_geo_ld(m1); w.n1 = hadi_geo_n1(m1); w.n2 = hadi_geo_n2(m2); w.pj = hadi_geo_pj(m2);
-  const HadiSmemLayout lay = hadi_smem_layout(m1, m2, w.ld, w.n1, w.n2, w.pj, RING, GLOBAL);
+  const HadiSmemLayout lay = hadi_smem_layout(m1, m2, w.ld, w.n1, w.n2, w.pj, FEED == 1, GLOBAL);
   char* sbase = reinterpret_cast<char*>(smem);
   double* scratch = L.scratch + (size_t)blockIdx.x * L.scratch_stride;
   const HadiScratchLayout gl = hadi_scratch_layout(m1, m2, w.ld, w.pj, GLOBAL, GLOBAL && L.scheme == 1);
@@ -297,11 +301,17 @@ __global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch
 
   // factor feed of phase S1
   const int ncw = (m2 + 1 + 31) / 32;  // solver warps
-  typename std::conditional<RING, HadiRingFeed, HadiDirectFeed>::type feed;
+  // FEED: 0 plain loads, 1 TMA ring + mbarriers (one producer thread), 3 plain loads behind L1 prefetches
+  typename std::conditional<FEED == 1, HadiRingFeed,
+      typename std::conditional<FEED == 3, HadiPrefetchFeed, HadiDirectFeed>::type>::type feed;
   feed.fM = w.fM;
   feed.fB = w.fB;
   feed.pj = w.pj;
-  if constexpr (RING) {
+  if constexpr (FEED == 3) {
+    feed.m1 = m1;
+    feed.j = 0;
+  }
+  if constexpr (FEED == 1) {
     feed.m1 = m1;
     feed.prod_tid = 32 * ncw;
     feed.ring = reinterpret_cast<double*>(sbase + lay.ring);
@@ -375,7 +385,7 @@ __global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch
     HADI_TICK(6)
   }
 #ifdef HADI_PHASE_TIMING
-  if constexpr (RING) tacc[6] = feed.wait_cycles;   // slot 6 reports the ring wait of solver thread 0
+  if constexpr (FEED == 1) tacc[6] = feed.wait_cycles;   // slot 6 reports the ring wait of solver thread 0
   if (tid == 0 && L.prof != nullptr)
     for (int k = 0; k < 8; ++k) L.prof[(size_t)blockIdx.x * 8 + k] = tacc[k];
 #endif
@@ -389,17 +399,27 @@ __global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch
 // 3: any grid with m1+1 <= 1024 that fits shared memory, run-time dimensions, one CTA per SM
 // 5: any grid with m1+1 <= 1024: U and Y in L2-resident global scratch, tables in shared memory, TMA ring for
 //    the A1 factors, one CTA per SM (grids beyond shared memory, e.g. 401 x 201; all Craig-Sneyd solves)
-#define HADI_VARIANTS(X)               \
-  X(0, 320, 2, 100, 50, true, false)  \
-  X(1, 256, 3, 50, 25, true, false)   \
-  X(2, 416, 2, 0, 0, false, false)    \
-  X(3, 1024, 1, 0, 0, false, false)   \
-  X(4, 320, 2, 100, 50, false, false) \
-  X(5, 1024, 1, 0, 0, true, true)
+// Factor feed of the grid-specialised variants, measured on B200 (round 1): at 101x51 plain loads (2.68 ms for
+// config 2) beat the TMA ring (2.78 ms: mbarrier try_wait costs ~90 cycles per chunk on the dependent chain),
+// per-thread cp.async stages (2.97 ms) and L1 prefetches (2.87 ms); at 51x26 the L1 prefetch wins.
+#ifndef HADI_FEED0
+#define HADI_FEED0 0
+#endif
+#ifndef HADI_FEED1
+#define HADI_FEED1 3
+#endif
+#define HADI_VARIANTS(X)                 \
+  X(0, 320, 2, 100, 50, HADI_FEED0, false) \
+  X(1, 256, 3, 50, 25, HADI_FEED1, false)  \
+  X(2, 416, 2, 0, 0, 0, false)          \
+  X(3, 1024, 1, 0, 0, 0, false)         \
+  X(4, 320, 2, 100, 50, 1, false)       \
+  X(5, 1024, 1, 0, 0, 1, true)
 
 struct VariantInfo {
   int threads, m1, m2;
-  bool ring, global_state;
+  int feed;   // 0 plain loads, 1 TMA ring, 3 plain loads behind L1 prefetches
+  bool global_state;
   const void* fn;
 };
 const VariantInfo* variants() {
@@ -430,8 +450,8 @@ int hadi_douglas_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj
     if (need_global && !v[k].global_state) continue;
     if (v[k].m1 != 0 && (v[k].m1 != m1 || v[k].m2 != m2)) continue;
     if (v[k].threads < m1 + 1 || v[k].threads - 1 <= m2) continue;
-    if (v[k].ring && v[k].threads <= 32 * ((m2 + 1 + 31) / 32)) continue;   // needs a producer thread past the solver warps
-    smem = hadi_smem_layout(m1, m2, ld, n1, n2, pj, v[k].ring, v[k].global_state).total;
+    if (v[k].feed == 1 && v[k].threads <= 32 * ((m2 + 1 + 31) / 32)) continue;   // needs a producer thread past the solver warps
+    smem = hadi_smem_layout(m1, m2, ld, n1, n2, pj, v[k].feed == 1, v[k].global_state).total;
     if (smem > (size_t)max_smem) continue;
     pick = k;
     break;
