@@ -86,6 +86,13 @@ __device__ __forceinline__ void hadi_dbg_check_lam(const HadiLaunch& L, const Ha
 
 // One item, payoff to price.  Returns (CTA-uniform) whether any guarded division left its fast-path
 // range; EXACT = true compiles every division as IEEE '/'.
+// FEED == 4: co-operative S1 / pipelined S2 of hadi_phases_fast.cuh (grid-specialised variants only)
+struct HadiCoopFeed : HadiDirectFeed {
+  static constexpr bool kCoop = true;
+};
+template <class F> struct hadi_is_coop { static constexpr bool value = false; };
+template <> struct hadi_is_coop<HadiCoopFeed> { static constexpr bool value = true; };
+
 template <int NT, int M1, int M2, bool EXACT, class Feed>
 __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiItem& it, HadiView& w, Feed& feed,
                                                 int tid, long long* tacc, long long& tlast) {
@@ -98,6 +105,11 @@ __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiI
   unsigned bad = 0;
 
   hadi_phase_tables(it, w, sg, vg, tid, NT);
+  if constexpr (hadi_is_coop<Feed>::value && M1 > 0) {
+    // staged / consumed block counters of the co-operative S1 (hadi_phases_fast.cuh)
+    if (tid < 2 * hadi_co_warps(M2))
+      reinterpret_cast<int*>(w.stg + hadi_co_warps(M2) * hadi_co_warp_doubles())[tid] = 0;
+  }
   __syncthreads();
   hadi_phase_factor(it, w, vg, tid, NT, NT - 1);
   if constexpr (Feed::kTma) {
@@ -122,6 +134,7 @@ __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiI
       }
     }
   }
+  if constexpr (hadi_is_coop<Feed>::value && M1 > 0) hadi_fast_prestage<M1, M2>(w, tid, 0);
   __syncthreads();
   if constexpr (Feed::kTma) {
     if (feed.producer(tid)) feed.produce(0, it.N, 0);  // first chunks are in flight before step 1
@@ -157,7 +170,11 @@ __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiI
     __syncthreads();
     HADI_TICK(2)
     HADI_STOP(4)
-    hadi_phase_solve_a1<M1, M2, EXACT>(it, w, e0, e1, n, tid, NT, feed, bad, &tacc[1]);
+    if constexpr (hadi_is_coop<Feed>::value && M1 > 0) {
+      hadi_fast_solve_a1<M1, M2, EXACT>(it, w, n - 1, tid, bad, &tacc[1]);
+    } else {
+      hadi_phase_solve_a1<M1, M2, EXACT>(it, w, e0, e1, n, tid, NT, feed, bad, &tacc[1]);
+    }
     __syncthreads();
     HADI_TICK(3)
     HADI_STOP(5)
@@ -165,7 +182,14 @@ __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiI
     __syncthreads();
     HADI_TICK(7)
     HADI_STOP(6)
-    hadi_phase_solve_a2<M1, M2, EXACT>(it, w, tid, NT, bad);
+    if constexpr (M1 > 0) {
+      hadi_fast_solve_a2<M1, M2, EXACT>(w, tid, bad);   // grid-specialised variants: pipelined, branch-free
+      if constexpr (hadi_is_coop<Feed>::value) {
+        if (n < it.N) hadi_fast_prestage<M1, M2>(w, tid, n);   // the feeder warps are idle in this phase
+      }
+    } else {
+      hadi_phase_solve_a2<M1, M2, EXACT>(it, w, tid, NT, bad);
+    }
     __syncthreads();
     HADI_TICK(4)
     HADI_STOP(7)
@@ -280,8 +304,14 @@ __global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch
   HadiView w;
   w.m1 = m1; w.m2 = m2; w.P = (m1 + 1) * (m2 + 1);
   w.ld = hadi_geo_ld(m1); w.n1 = hadi_geo_n1(m1); w.n2 = hadi_geo_n2(m2); w.pj = hadi_geo_pj(m2);
-  const HadiSmemLayout lay = hadi_smem_layout(m1, m2, w.ld, w.n1, w.n2, w.pj, FEED == 1, GLOBAL);
+  const HadiSmemLayout lay = hadi_smem_layout(m1, m2, w.ld, w.n1, w.n2, w.pj, FEED == 1, GLOBAL, FEED == 4);
   char* sbase = reinterpret_cast<char*>(smem);
+  if constexpr (FEED == 4) {
+    w.co_pi = hadi_co_pi(m1);
+    w.nti = HADI_LEAN ? TI_CORE : TI_COUNT;
+    w.zmask = (L.n_items < 0) ? ~0u : 0u;
+    w.stg = reinterpret_cast<double*>(sbase + lay.ring);
+  }
   double* scratch = L.scratch + (size_t)blockIdx.x * L.scratch_stride;
   const HadiScratchLayout gl = hadi_scratch_layout(m1, m2, w.ld, w.pj, GLOBAL, GLOBAL && L.scheme == 1);
   // the working set: shared memory, or (GLOBAL) L2-resident global scratch for grids beyond it
@@ -301,9 +331,11 @@ __global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch
 
   // factor feed of phase S1
   const int ncw = (m2 + 1 + 31) / 32;  // solver warps
-  // FEED: 0 plain loads, 1 TMA ring + mbarriers (one producer thread), 3 plain loads behind L1 prefetches
+  // FEED: 0 plain loads, 1 TMA ring + mbarriers (one producer thread), 3 plain loads behind L1 prefetches,
+  //       4 co-operative warps (hadi_phases_fast.cuh)
   typename std::conditional<FEED == 1, HadiRingFeed,
-      typename std::conditional<FEED == 3, HadiPrefetchFeed, HadiDirectFeed>::type>::type feed;
+      typename std::conditional<FEED == 3, HadiPrefetchFeed,
+          typename std::conditional<FEED == 4, HadiCoopFeed, HadiDirectFeed>::type>::type>::type feed;
   feed.fM = w.fM;
   feed.fB = w.fB;
   feed.pj = w.pj;
@@ -413,12 +445,12 @@ __global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch
   X(1, 256, 3, 50, 25, HADI_FEED1, false)  \
   X(2, 416, 2, 0, 0, 0, false)          \
   X(3, 1024, 1, 0, 0, 0, false)         \
-  X(4, 320, 2, 100, 50, 1, false)       \
+  X(4, 320, 2, 100, 50, 4, false)       \
   X(5, 1024, 1, 0, 0, 1, true)
 
 struct VariantInfo {
   int threads, m1, m2;
-  int feed;   // 0 plain loads, 1 TMA ring, 3 plain loads behind L1 prefetches
+  int feed;   // 0 plain loads, 1 TMA ring, 3 plain loads behind L1 prefetches, 4 co-operative warps
   bool global_state;
   const void* fn;
 };
@@ -451,7 +483,7 @@ int hadi_douglas_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj
     if (v[k].m1 != 0 && (v[k].m1 != m1 || v[k].m2 != m2)) continue;
     if (v[k].threads < m1 + 1 || v[k].threads - 1 <= m2) continue;
     if (v[k].feed == 1 && v[k].threads <= 32 * ((m2 + 1 + 31) / 32)) continue;   // needs a producer thread past the solver warps
-    smem = hadi_smem_layout(m1, m2, ld, n1, n2, pj, v[k].feed == 1, v[k].global_state).total;
+    smem = hadi_smem_layout(m1, m2, ld, n1, n2, pj, v[k].feed == 1, v[k].global_state, v[k].feed == 4).total;
     if (smem > (size_t)max_smem) continue;
     pick = k;
     break;

@@ -2,6 +2,10 @@
 #pragma once
 #include <cstddef>
 #include "hadi_phases.cuh"
+#include "hadi_phases_fast.cuh"
+#ifndef HADI_LEAN
+#define HADI_LEAN 1   /* co-operative variants keep only the TI_CORE per-column tables in shared memory */
+#endif
 
 struct HadiLaunch {
   int m1, m2, ld, n1, n2, pj;
@@ -40,19 +44,20 @@ struct HadiSmemLayout {
   size_t U, Y, ti, tj, divk, ring, bars, total;
 };
 HADI_HD HadiSmemLayout hadi_smem_layout(int m1, int m2, int ld, int n1, int n2, int pj, bool ring,
-                                        bool global_state = false) {
+                                        bool global_state = false, bool coop = false) {
   (void)m1;
   HadiSmemLayout s;
   size_t off = 0;
   // U carries HADI_HALO zero rows above and below and one spare word at either end
   s.U = off; if (!global_state) off += sizeof(double) * ((size_t)(m2 + 1 + 2 * HADI_HALO) * ld + 2);
   s.Y = off; if (!global_state) off += sizeof(double) * (size_t)(m2 + 1) * ld;
-  s.ti = off; off += sizeof(double) * (size_t)TI_COUNT * n1;
+  s.ti = off; off += sizeof(double) * (size_t)((coop && HADI_LEAN) ? TI_CORE : TI_COUNT) * n1;   // lean tables in the co-operative variants
   s.tj = off; off += sizeof(double) * (size_t)TJ_COUNT * n2;
   s.divk = off; off += sizeof(int) * (size_t)n1;
   off = (off + 127) & ~size_t(127);
   s.ring = off;
   if (ring) off += sizeof(double) * (size_t)HADI_NS * HADI_KF * pj;
+  if (coop) off += (size_t)hadi_co_stage_bytes(m2);
   s.bars = off;
   if (ring) off += sizeof(unsigned long long) * 2 * HADI_NS;
   s.total = off + 16;
@@ -67,8 +72,11 @@ HADI_HD HadiScratchLayout hadi_scratch_layout(int m1, int m2, int ld, int pj, bo
   HadiScratchLayout s;
   size_t off = 0;
   const size_t arr = (size_t)(m2 + 1) * (size_t)ld;
-  s.fM = off; off += (size_t)m1 * pj; off = (off + 15) & ~size_t(15);
-  s.fB = off; off += (size_t)2 * m1 * pj; off = (off + 15) & ~size_t(15);
+  // sized for either factor layout: classic [m1][pj] or co-operative [13*ceil((m2+1)/13)][(m1+7)&~7]
+  const size_t co = (size_t)(((m2 + 13) / 13) * 13) * (size_t)((m1 + 7) & ~7);
+  const size_t fsz = ((size_t)m1 * pj > co) ? (size_t)m1 * pj : co;
+  s.fM = off; off += fsz; off = (off + 15) & ~size_t(15);
+  s.fB = off; off += 2 * fsz; off = (off + 15) & ~size_t(15);
   s.lam = off; off += arr; off = (off + 15) & ~size_t(15);
   s.U = off; if (global_state) off += (size_t)(m2 + 1 + 2 * HADI_HALO) * ld + 2; off = (off + 15) & ~size_t(15);
   s.Y = off; if (global_state) off += arr; off = (off + 15) & ~size_t(15);
