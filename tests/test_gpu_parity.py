@@ -38,6 +38,29 @@ def test_native_library_is_the_one_running(hadi, ctx):
         assert "libhadi.so" in f.read()
 
 
+def test_cooperative_s1_variant_matches_oracle_bitwise(hadi, ctx, oracle, monkeypatch):
+    """Kernel variant 4 (101x51): chain warps fed by feeder warps through the flag-ordered staging ring
+    (csrc/hadi_phases_fast.cuh).  Not the default yet (not faster), but it must stay bit-exact: single solves of
+    all four reference functions, and a batch larger than the persistent grid (no stale staging between items)."""
+    monkeypatch.setenv("HADI_FORCE_VARIANT", "4")
+    for style in (0, 1):
+        for dv in (None, DIVS):
+            o = oracle.solve(93.0, 20, 1.0 / 20, m1=100, m2=50, theta=0.8, style=style, divs=dv, payoff_put=0, **BASE)
+            g = solve_gpu(hadi, ctx, [93.0], 20, 1.0, 100, 50, style, 0, dv, BASE)
+            assert g["prices"][0] == o["price"]
+            assert np.array_equal(g["U"][0], o["U"])
+            if style:
+                assert np.array_equal(g["lambda"][0], o["lambda"])
+    strikes = [80.0 + 0.05 * k for k in range(700)]
+    mdl = hadi.make_model(**BASE)
+    num = hadi.make_numerics(100, 50, 0.8, 1, 0, hadi.DOUGLAS, DIVS)
+    pts, n = hadi.make_points(strikes, 1.0, 10)
+    a = ctx.price_batch(mdl, num, pts, n)["prices"]
+    monkeypatch.setenv("HADI_FORCE_VARIANT", "0")
+    b = ctx.price_batch(mdl, num, pts, n)["prices"]
+    assert np.array_equal(a, b)
+
+
 @pytest.mark.parametrize("m1,m2,N", [(50, 25, 20), (100, 50, 20), (20, 10, 7), (64, 32, 9), (40, 40, 6), (300, 12, 5)])
 def test_single_solves_match_oracle_bitwise(hadi, ctx, oracle, m1, m2, N):
     """Specialised variants (101x51, 51x26) and the run-time-dimension variants, all four reference
