@@ -304,11 +304,11 @@ __global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch
   HadiView w;
   w.m1 = m1; w.m2 = m2; w.P = (m1 + 1) * (m2 + 1);
   w.ld = hadi_geo_ld(m1); w.n1 = hadi_geo_n1(m1); w.n2 = hadi_geo_n2(m2); w.pj = hadi_geo_pj(m2);
-  const HadiSmemLayout lay = hadi_smem_layout(m1, m2, w.ld, w.n1, w.n2, w.pj, FEED == 1, GLOBAL, FEED == 4);
+  const HadiSmemLayout lay = hadi_smem_layout(m1, m2, w.ld, w.n1, w.n2, w.pj, FEED == 1, GLOBAL, FEED == 4, M1 > 0);
+  if constexpr (M1 > 0) w.nti = HADI_LEAN ? TI_CORE : TI_COUNT;
   char* sbase = reinterpret_cast<char*>(smem);
   if constexpr (FEED == 4) {
     w.co_pi = hadi_co_pi(m1);
-    w.nti = HADI_LEAN ? TI_CORE : TI_COUNT;
     w.zmask = (L.n_items < 0) ? ~0u : 0u;
     w.stg = reinterpret_cast<double*>(sbase + lay.ring);
   }
@@ -385,7 +385,11 @@ __global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch
 #ifdef HADI_FORCE_EXACT
       hadi_solve_item<NT, M1, M2, true>(L, it, w, feed, tid, tacc, tlast);
 #else
+#ifdef HADI_NO_RERUN   /* timing experiments only */
+      if (hadi_solve_item<NT, M1, M2, false>(L, it, w, feed, tid, tacc, tlast) && L.n_items < 0) {
+#else
       if (hadi_solve_item<NT, M1, M2, false>(L, it, w, feed, tid, tacc, tlast)) {
+#endif
         if (tid == 0 && L.prof != nullptr) atomicAdd((unsigned long long*)&L.prof[(size_t)gridDim.x * 8], 1ULL);
         hadi_solve_item<NT, M1, M2, true>(L, it, w, feed, tid, tacc, tlast);
       }
@@ -483,7 +487,7 @@ int hadi_douglas_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj
     if (v[k].m1 != 0 && (v[k].m1 != m1 || v[k].m2 != m2)) continue;
     if (v[k].threads < m1 + 1 || v[k].threads - 1 <= m2) continue;
     if (v[k].feed == 1 && v[k].threads <= 32 * ((m2 + 1 + 31) / 32)) continue;   // needs a producer thread past the solver warps
-    smem = hadi_smem_layout(m1, m2, ld, n1, n2, pj, v[k].feed == 1, v[k].global_state, v[k].feed == 4).total;
+    smem = hadi_smem_layout(m1, m2, ld, n1, n2, pj, v[k].feed == 1, v[k].global_state, v[k].feed == 4, v[k].m1 != 0).total;
     if (smem > (size_t)max_smem) continue;
     pick = k;
     break;

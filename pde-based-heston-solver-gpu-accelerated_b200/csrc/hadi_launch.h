@@ -4,7 +4,7 @@
 #include "hadi_phases.cuh"
 #include "hadi_phases_fast.cuh"
 #ifndef HADI_LEAN
-#define HADI_LEAN 1   /* co-operative variants keep only the TI_CORE per-column tables in shared memory */
+#define HADI_LEAN 1   /* grid-specialised variants keep only the TI_CORE per-column tables in shared memory */
 #endif
 
 struct HadiLaunch {
@@ -44,14 +44,14 @@ struct HadiSmemLayout {
   size_t U, Y, ti, tj, divk, ring, bars, total;
 };
 HADI_HD HadiSmemLayout hadi_smem_layout(int m1, int m2, int ld, int n1, int n2, int pj, bool ring,
-                                        bool global_state = false, bool coop = false) {
+                                        bool global_state = false, bool coop = false, bool lean = false) {
   (void)m1;
   HadiSmemLayout s;
   size_t off = 0;
   // U carries HADI_HALO zero rows above and below and one spare word at either end
   s.U = off; if (!global_state) off += sizeof(double) * ((size_t)(m2 + 1 + 2 * HADI_HALO) * ld + 2);
   s.Y = off; if (!global_state) off += sizeof(double) * (size_t)(m2 + 1) * ld;
-  s.ti = off; off += sizeof(double) * (size_t)((coop && HADI_LEAN) ? TI_CORE : TI_COUNT) * n1;   // lean tables in the co-operative variants
+  s.ti = off; off += sizeof(double) * (size_t)((lean && HADI_LEAN) ? TI_CORE : TI_COUNT) * n1;   // lean tables in the grid-specialised variants
   s.tj = off; off += sizeof(double) * (size_t)TJ_COUNT * n2;
   s.divk = off; off += sizeof(int) * (size_t)n1;
   off = (off + 127) & ~size_t(127);
