@@ -178,12 +178,20 @@ __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiI
     __syncthreads();
     HADI_TICK(3)
     HADI_STOP(5)
+#ifdef HADI_SPLIT_R
     hadi_phase_rhs2<M1, M2>(it, w, e0, e1, tid, NT);
     __syncthreads();
+#else
+    if constexpr (M1 == 0) {
+      hadi_phase_rhs2<M1, M2>(it, w, e0, e1, tid, NT);
+      __syncthreads();
+    }
+#endif
     HADI_TICK(7)
     HADI_STOP(6)
     if constexpr (M1 > 0) {
-      hadi_fast_solve_a2<M1, M2, EXACT>(w, tid, bad);   // grid-specialised variants: pipelined, branch-free
+      // grid-specialised variants: phase R is folded into the forward sweep of the column solve
+      hadi_fast_solve_a2<M1, M2, EXACT>(it, w, e0, e1, tid, bad);
       if constexpr (hadi_is_coop<Feed>::value) {
         if (n < it.N) hadi_fast_prestage<M1, M2>(w, tid, n);   // the feeder warps are idle in this phase
       }
@@ -321,6 +329,7 @@ __global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch
   w.ti = reinterpret_cast<double*>(sbase + lay.ti);
   w.tj = reinterpret_cast<double*>(sbase + lay.tj);
   w.divk = reinterpret_cast<int*>(sbase + lay.divk);
+  if constexpr (M1 > 0) w.tjp = reinterpret_cast<double*>(sbase + lay.tjp);
   w.fM = scratch + gl.fM;
   w.fB = scratch + gl.fB;
   w.lam = scratch + gl.lam;

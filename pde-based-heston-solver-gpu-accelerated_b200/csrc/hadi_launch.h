@@ -41,7 +41,7 @@ struct HadiPlan {
 
 // shared memory layout of the Douglas kernel (offsets in bytes from the dynamic smem base)
 struct HadiSmemLayout {
-  size_t U, Y, ti, tj, divk, ring, bars, total;
+  size_t U, Y, ti, tj, tjp, divk, ring, bars, total;
 };
 HADI_HD HadiSmemLayout hadi_smem_layout(int m1, int m2, int ld, int n1, int n2, int pj, bool ring,
                                         bool global_state = false, bool coop = false, bool lean = false) {
@@ -53,6 +53,9 @@ HADI_HD HadiSmemLayout hadi_smem_layout(int m1, int m2, int ld, int n1, int n2, 
   s.Y = off; if (!global_state) off += sizeof(double) * (size_t)(m2 + 1) * ld;
   s.ti = off; off += sizeof(double) * (size_t)((lean && HADI_LEAN) ? TI_CORE : TI_COUNT) * n1;   // lean tables in the grid-specialised variants
   s.tj = off; off += sizeof(double) * (size_t)TJ_COUNT * n2;
+  // packed per-row records {L2, L1, D0, U1, U2, F, G, MM} of the fused R + S2 phase (grid-specialised variants)
+  off = (off + 15) & ~size_t(15);
+  s.tjp = off; if (lean) off += sizeof(double) * (size_t)8 * n2;
   s.divk = off; off += sizeof(int) * (size_t)n1;
   off = (off + 127) & ~size_t(127);
   s.ring = off;

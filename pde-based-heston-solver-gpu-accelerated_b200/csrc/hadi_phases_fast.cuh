@@ -265,36 +265,72 @@ __device__ __forceinline__ void hadi_fast_solve_a1(const HadiItem& it, const Had
 }
 
 // ----------------------------------------------------------------------------------------------
-// S2: (I - theta*dt*A2) U = Y1, one thread per s-column on the natural layout (stride LD).
+// R + S2 fused: (I - theta*dt*A2) U = Y1 + theta*dt*(b2*e1 - (A2 U + b2*e0)), one thread per s-column on the
+// natural layout (stride LD).  Phase R (src/device_solver.hpp:254-260) is point-wise in the column, so the
+// thread that is about to start the dependent forward chain of node j forms that node's right-hand side on
+// the way: A2 U from a five-row register window of its own column of U (old solution: the back substitution
+// below is what overwrites it, after the forward sweep has read all of it), with the per-row coefficients
+// coming as packed 64-byte records {L2, L1, D0, U1, U2, F, G, MM} (4 broadcast LDS.128 per node instead of 8
+// LDS.64).  This removes one pass over the grid and one __syncthreads() per step; the extra 15 FP64 operations
+// per node ride in the issue slots the 4-deep dependent chain leaves free.  Same operations, same order as
+// hadi_phase_rhs2 + hadi_phase_solve_a2.
+#ifdef HADI_SPLIT_R
+#define HADI_FUSE_R 0
+#else
+#define HADI_FUSE_R 1
+#endif
 template <int M1, int M2, bool EXACT>
-__device__ __forceinline__ void hadi_fast_solve_a2(const HadiView& w, int tid, unsigned& bad) {
-  constexpr int LD = hadi_geo_ld(M1), N2 = hadi_geo_n2(M2);
-  constexpr int PF = 3;
+__device__ __forceinline__ void hadi_fast_solve_a2(const HadiItem& it, const HadiView& w, double e0, double e1,
+                                                   int tid, unsigned& bad) {
+  constexpr int LD = hadi_geo_ld(M1), N1 = hadi_geo_n1(M1), N2 = hadi_geo_n2(M2);
+  constexpr int PF = 2;
   if (tid > M1) return;
-  const double* F = w.tj + TJ_F * N2;
-  const double* G = w.tj + TJ_G * N2;
-  const double* MM = w.tj + TJ_MM * N2;
   const double* CP = w.tj + TJ_CP * N2;
   const double* C2P = w.tj + TJ_C2P * N2;
+  const double2* rec = reinterpret_cast<const double2*>(w.tjp);
   double* Yc = w.Y + tid;
   double* Uc = w.U + tid;
+  const double c = w.c;
+  const double b2v = w.ti[TI_B2V * N1 + tid];
+  (void)it;
   // ---- forward sweep: d_0 = b_0 / impl_main(0);  d_j = (b_j - f_j d_{j-1} - g_j d_{j-2}) * m_j
-  double bq[PF], fq[PF], gq[PF], mq[PF];
+  // operand queue, PF nodes ahead: y_j, U[j+2] (the window's new row) and the row record
+  double yq[PF + 1], uq[PF + 1];
+  double2 ra[PF + 1], rb[PF + 1], rc[PF + 1], rd[PF + 1];
 #pragma unroll
-  for (int k = 0; k < PF; ++k) {
-    bq[k] = Yc[(1 + k) * LD]; fq[k] = F[1 + k]; gq[k] = G[1 + k]; mq[k] = MM[1 + k];
+  for (int k = 0; k <= PF; ++k) {
+    yq[k] = Yc[k * LD];
+    uq[k] = HADI_FUSE_R ? Uc[(k + 2) * LD] : 0.0;
+    ra[k] = rec[4 * k]; rb[k] = rec[4 * k + 1]; rc[k] = rec[4 * k + 2]; rd[k] = rec[4 * k + 3];
   }
-  double d1 = hadi_div<EXACT>(Yc[0], MM[0], G[0], bad);
-  double d2 = 0.0;
-  Yc[0] = d1;
+  double um2 = 0.0, um1 = 0.0, u0 = 0.0, up1 = 0.0;     // U[j-2], U[j-1], U[j], U[j+1] (halo rows are zero)
+  if (HADI_FUSE_R) { u0 = Uc[0]; up1 = Uc[LD]; }
+  double d1 = 0.0, d2 = 0.0;
 #pragma unroll
-  for (int j = 1; j <= M2; ++j) {
-    const int s = (j - 1) % PF;
-    const double bc = bq[s], fc = fq[s], gc = gq[s], mc = mq[s];
-    if (j + PF <= M2) {
-      bq[s] = Yc[(j + PF) * LD]; fq[s] = F[j + PF]; gq[s] = G[j + PF]; mq[s] = MM[j + PF];
+  for (int j = 0; j <= M2; ++j) {
+    const int s = j % (PF + 1);
+    const double yc = yq[s], up2 = uq[s];
+    const double2 A = ra[s], B = rb[s], C = rc[s], D = rd[s];   // {L2,L1} {D0,U1} {U2,F} {G,MM}
+    if (j + PF + 1 <= M2) {
+      const int f = j + PF + 1;
+      yq[s] = Yc[f * LD];
+      uq[s] = HADI_FUSE_R ? Uc[(f + 2) * LD] : 0.0;
+      ra[s] = rec[4 * f]; rb[s] = rec[4 * f + 1]; rc[s] = rec[4 * f + 2]; rd[s] = rec[4 * f + 3];
     }
-    const double d = (bc - fc * d1 - gc * d2) * mc;
+    double bc = yc;
+    if (HADI_FUSE_R) {
+      double r2 = A.x * um2 + A.y * um1 + B.x * u0 + B.y * up1;
+      r2 += C.x * up2;
+      const double b2 = (j == M2) ? b2v : 0.0;
+      bc = yc + c * (b2 * e1 - (r2 + b2 * e0));
+      um2 = um1; um1 = u0; u0 = up1; up1 = up2;
+    }
+    double d;
+    if (j == 0) {
+      d = hadi_div<EXACT>(bc, D.y, D.x, bad);       // row 0: MM[0] holds impl_main(0), G[0] its prepared reciprocal
+    } else {
+      d = (bc - C.y * d1 - D.x * d2) * D.y;
+    }
     Yc[j * LD] = d;
     d2 = d1;
     d1 = d;
@@ -303,20 +339,21 @@ __device__ __forceinline__ void hadi_fast_solve_a2(const HadiView& w, int tid, u
   // (compiler fence: with every address static the compiler would otherwise forward all m2+1 stored d_j to
   //  the loads below, i.e. keep them live in registers and spill them to local memory)
   asm volatile("" ::: "memory");
-  double dq[PF], cq[PF], eq[PF];
+  constexpr int PB = 3;
+  double dq[PB], cq[PB], eq[PB];
   dq[0] = d1; cq[0] = CP[M2]; eq[0] = C2P[M2];
   dq[1] = d2; cq[1] = CP[M2 - 1]; eq[1] = C2P[M2 - 1];
 #pragma unroll
-  for (int k = 2; k < PF; ++k) {
+  for (int k = 2; k < PB; ++k) {
     dq[k] = Yc[(M2 - k) * LD]; cq[k] = CP[M2 - k]; eq[k] = C2P[M2 - k];
   }
   double x1 = 0.0, x2 = 0.0;
 #pragma unroll
   for (int e = 0; e <= M2; ++e) {
-    const int s = e % PF;
+    const int s = e % PB;
     const double dc = dq[s], cc = cq[s], c2 = eq[s];
-    if (e + PF <= M2) {
-      dq[s] = Yc[(M2 - e - PF) * LD]; cq[s] = CP[M2 - e - PF]; eq[s] = C2P[M2 - e - PF];
+    if (e + PB <= M2) {
+      dq[s] = Yc[(M2 - e - PB) * LD]; cq[s] = CP[M2 - e - PB]; eq[s] = C2P[M2 - e - PB];
     }
     const double xv = dc - cc * x1 - c2 * x2;
     x2 = x1;
