@@ -325,9 +325,19 @@ int hadi_batch_create(hadi_ctx* ctx, const hadi_model* model, const hadi_numeric
   HadiPlan plan;
   {
     const bool cs = num->scheme == HADI_CRAIG_SNEYD;
-    int prc = hadi_douglas_plan(ctx->device, m1, m2, g.ld, g.n1, g.n2, g.pj, cs, &plan);
+    // few large solves: spread each over a thread-block cluster (needs the global working set; the dividend
+    // jump keeps per-CTA tables and stays on the one-CTA-per-solve kernels)
+    const int n_it = (item_end < 0 ? n * n_columns(mode) : item_end) - item_begin;
+    const bool few = n_it * HADI_CLUSTER <= 148 && num->num_dividends == 0;
+    int prc = hadi_douglas_plan(ctx->device, m1, m2, g.ld, g.n1, g.n2, g.pj, cs, &plan, few);
     // grids beyond shared memory run on the global-state kernel (working set in L2-resident scratch)
-    if (prc < 0 && !cs) prc = hadi_douglas_plan(ctx->device, m1, m2, g.ld, g.n1, g.n2, g.pj, true, &plan);
+    if (prc < 0 && !cs) prc = hadi_douglas_plan(ctx->device, m1, m2, g.ld, g.n1, g.n2, g.pj, true, &plan, few);
+    // a Douglas grid that only the global-state kernel takes: same choice between one CTA and one cluster per solve
+    if (prc == 0 && plan.global_state && plan.cluster <= 1 && few) {
+      HadiPlan cplan;
+      if (hadi_douglas_plan(ctx->device, m1, m2, g.ld, g.n1, g.n2, g.pj, true, &cplan, true) == 0 && cplan.cluster > 1)
+        plan = cplan;
+    }
     if (prc < 0) return fail(ctx, HADI_ERR_SMEM, "grid too large: m1+1 <= 1024 and the coefficient tables must fit shared memory");
     if (prc > 0) return cuda_fail(ctx, (cudaError_t)prc, "kernel plan");
   }
@@ -440,10 +450,11 @@ int hadi_batch_create(hadi_ctx* ctx, const hadi_model* model, const hadi_numeric
 
   b->plan = plan;
   b->grid_ctas = std::max(1, std::min(n_items, plan.ctas_per_sm * plan.sm_count));
+  if (plan.cluster > 1) b->grid_ctas = plan.cluster * std::max(1, std::min(n_items, plan.sm_count / plan.cluster));
   if (const char* cap = getenv("HADI_MAX_CTAS"))  // development aid: cap the persistent grid
     if (atoi(cap) > 0) b->grid_ctas = std::min(b->grid_ctas, atoi(cap));
   const size_t stride = hadi_scratch_layout(m1, m2, g.ld, g.pj, plan.global_state, num->scheme == HADI_CRAIG_SNEYD).total;
-  double* d_scratch = (double*)take(sizeof(double) * stride * (size_t)b->grid_ctas, false);
+  double* d_scratch = (double*)take(sizeof(double) * stride * (size_t)(b->grid_ctas / std::max(1, plan.cluster)), false);
   if (!h_stage || !d_stage || !b->h_values || !d_values || !d_counter || !d_scratch) {
     release_all();
     return HADI_ERR_NOMEM;

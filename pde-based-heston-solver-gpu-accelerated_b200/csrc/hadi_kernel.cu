@@ -436,6 +436,148 @@ __global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch
 #endif
 }
 
+// ---- cluster kernel -------------------------------------------------------------------------------
+// One solve on a thread-block CLUSTER: grids beyond shared memory (e.g. 401 x 201, 645 KB per array) keep their
+// working arrays in global scratch, so nothing ties a solve to one SM.  The HADI_CLUSTER CTAs of a cluster share
+// one scratch block; point-wise phases run over all their threads (same (i, q) mapping, 8 x 256 threads with up to 255 registers each), the
+// lines of the implicit solves are dealt round-robin to the CTAs (HadiView::line_mul / line_off), every CTA
+// keeps its own copy of the small coefficient tables in shared memory, and the phases are separated by
+// barrier.cluster (release / acquire at cluster scope: global writes of the other CTAs become visible and the
+// L1 is invalidated).  Same phase functions, same arithmetic: results are bit-identical to variant 5.
+__device__ __forceinline__ void hadi_csync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int NT, bool EXACT>
+__device__ __forceinline__ bool hadi_cluster_solve(const HadiLaunch& L, const HadiItem& it, HadiView& w,
+                                                   const HadiCsView& cs, int tid, int gtid, int gnt, int* mail) {
+  const int m1 = L.m1, m2 = L.m2;
+  const double* sg = L.s_pool + it.s_off;
+  const double* vg = L.v_pool + it.v_off;
+  const double* eg = L.e_pool + it.e_off;
+  w.c = it.theta * it.dt;
+  const double rdt = hadi_rcp_prep(it.dt);
+  unsigned bad = 0;
+  HadiDirectFeed feed;
+  feed.fM = w.fM; feed.fB = w.fB; feed.pj = w.pj;
+  hadi_phase_tables(it, w, sg, vg, tid, NT);          // per-CTA tables (the A2 scratch tables live in Y: every
+  hadi_csync();                                        // CTA writes the same values there)
+  hadi_phase_factor(it, w, vg, tid, NT, NT - 1);
+  hadi_csync();
+  {
+    const HadiMap mp = hadi_map(m1, m2, gtid, gnt);
+    if (mp.active) {
+      const double pay = hadi_ti(w, TI_PAY)[mp.i];
+      for (int j = mp.j0; j < mp.j1; ++j) {
+        w.U[j * w.ld + mp.i] = pay;
+        if (it.style == 1) {
+          w.lam[j * w.ld + mp.i] = 0.0;
+          w.Y[j * w.ld + mp.i] = 0.0;
+        }
+      }
+    }
+  }
+  hadi_csync();
+  for (int n = 1; n <= it.N; ++n) {
+    const double e0 = eg[n - 1], e1 = eg[n];
+    if (L.scheme == 1) {
+      hadi_cs_predict(it, w, cs, e0, e1, gtid, gnt);
+      hadi_csync();
+      hadi_phase_solve_a1<0, 0, EXACT>(it, w, e0, e1, 2 * n - 1, tid, NT, feed, bad, nullptr, 2 * it.N);
+      hadi_csync();
+      hadi_cs_rhs2(it, w, cs, e0, e1, gtid, gnt);
+      hadi_csync();
+      hadi_phase_solve_a2<0, 0, EXACT>(it, w, tid, NT, bad);
+      hadi_csync();
+      hadi_cs_correct(it, w, cs, e0, e1, gtid, gnt);
+      hadi_csync();
+      hadi_phase_solve_a1<0, 0, EXACT>(it, w, e0, e1, 2 * n, tid, NT, feed, bad, nullptr, 2 * it.N);
+      hadi_csync();
+      hadi_cs_rhs2(it, w, cs, e0, e1, gtid, gnt);
+      hadi_csync();
+      hadi_phase_solve_a2<0, 0, EXACT>(it, w, tid, NT, bad);
+      hadi_csync();
+    } else {
+      hadi_phase_explicit<0, 0>(it, w, e0, e1, gtid, gnt);
+      hadi_csync();
+      hadi_phase_solve_a1<0, 0, EXACT>(it, w, e0, e1, n, tid, NT, feed, bad, nullptr, 0);
+      hadi_csync();
+      hadi_phase_rhs2<0, 0>(it, w, e0, e1, gtid, gnt);
+      hadi_csync();
+      hadi_phase_solve_a2<0, 0, EXACT>(it, w, tid, NT, bad);
+      hadi_csync();
+      if (it.style == 1) {
+        hadi_phase_project<0, 0, EXACT, HADI_CHP>(it, w, rdt, gtid, gnt, bad);
+        hadi_csync();
+      }
+    }
+  }
+  // cluster-wide vote on the guarded divisions
+  if (__syncthreads_or((int)bad) != 0 && tid == 0) atomicOr(mail + 1, 1);
+  hadi_csync();
+  return *reinterpret_cast<volatile int*>(mail + 1) != 0;
+}
+
+template <int NT>
+__global__ void __cluster_dims__(HADI_CLUSTER, 1, 1) __launch_bounds__(NT, 1) hadi_cluster_kernel(const HadiLaunch L) {
+  extern __shared__ double smem[];
+  const int tid = threadIdx.x;
+  unsigned rank_u;
+  asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank_u));
+  const int rank = (int)rank_u;
+  const int cid = blockIdx.x / HADI_CLUSTER;
+  const int gtid = rank * NT + tid, gnt = HADI_CLUSTER * NT;
+  const int m1 = L.m1, m2 = L.m2;
+  HadiView w;
+  w.m1 = m1; w.m2 = m2; w.P = (m1 + 1) * (m2 + 1);
+  w.ld = hadi_geo_ld(m1); w.n1 = hadi_geo_n1(m1); w.n2 = hadi_geo_n2(m2); w.pj = hadi_geo_pj(m2);
+  w.line_mul = HADI_CLUSTER; w.line_off = rank;
+  w.ts_off = rank * TS_COUNT * w.n2;   // (8 x 18 x n2 doubles: far inside Y for any grid the kernel is chosen for)
+  const HadiSmemLayout lay = hadi_smem_layout(m1, m2, w.ld, w.n1, w.n2, w.pj, false, true);
+  char* sbase = reinterpret_cast<char*>(smem);
+  double* scratch = L.scratch + (size_t)cid * L.scratch_stride;
+  const HadiScratchLayout gl = hadi_scratch_layout(m1, m2, w.ld, w.pj, true, L.scheme == 1);
+  double* Ualloc = scratch + gl.U;
+  w.U = Ualloc + HADI_HALO * w.ld + 1;
+  w.Y = scratch + gl.Y;
+  w.ti = reinterpret_cast<double*>(sbase + lay.ti);
+  w.tj = reinterpret_cast<double*>(sbase + lay.tj);
+  w.divk = reinterpret_cast<int*>(sbase + lay.divk);
+  w.fM = scratch + gl.fM;
+  w.fB = scratch + gl.fB;
+  w.lam = scratch + gl.lam;
+  HadiCsView cs;
+  cs.Y0 = scratch + gl.Y0; cs.R0 = scratch + gl.R0; cs.R1 = scratch + gl.R1; cs.R2 = scratch + gl.R2;
+  int* mail = reinterpret_cast<int*>(scratch + gl.mail);
+  for (int k = gtid; k < (m2 + 1 + 2 * HADI_HALO) * w.ld + 2; k += gnt) Ualloc[k] = 0.0;
+  for (;;) {
+    if (gtid == 0) {
+      mail[0] = atomicAdd(L.counter, 1);
+      mail[1] = 0;
+    }
+    hadi_csync();
+    const int item = *reinterpret_cast<volatile int*>(mail);
+    if (item >= L.n_items) break;
+    const HadiItem it = L.items[item];
+    if (hadi_cluster_solve<NT, false>(L, it, w, cs, tid, gtid, gnt, mail)) {
+      if (gtid == 0 && L.prof != nullptr) atomicAdd((unsigned long long*)&L.prof[(size_t)gridDim.x * 8], 1ULL);
+      hadi_cluster_solve<NT, true>(L, it, w, cs, tid, gtid, gnt, mail);
+    }
+    if (gtid == 0) L.out_values[it.out] = w.U[it.idx_v * w.ld + it.idx_s];
+    if (L.out_U != nullptr || L.out_lam != nullptr) {
+      const HadiMap mp = hadi_map(m1, m2, gtid, gnt);
+      if (mp.active) {
+        for (int j = mp.j0; j < mp.j1; ++j) {
+          const size_t p = (size_t)it.out * w.P + (size_t)j * (m1 + 1) + mp.i;
+          if (L.out_U != nullptr) L.out_U[p] = w.U[j * w.ld + mp.i];
+          if (L.out_lam != nullptr && it.style == 1) L.out_lam[p] = w.lam[j * w.ld + mp.i];
+        }
+      }
+    }
+    hadi_csync();   // everyone is done with the mailbox, U and the tables before the next item
+  }
+}
+
 // ---- variants ----------------------------------------------------------------------------------
 // 0: 101 x 51 nodes (BASELINE configs 1, 2, 5): 320 threads = 3 row-chunks x 101 columns (+17),
 //    2 CTAs/SM, <= 102 registers (no spills: L1 is all but gone at this shared-memory carve-out)
@@ -476,10 +618,13 @@ const VariantInfo* variants() {
   return v;
 }
 constexpr int kNumVariants = 6;
+constexpr int kClusterVariant = 6;   // hadi_cluster_kernel: one solve per thread-block cluster
+constexpr int kClusterThreads = 256; // few threads, many registers: the generic phases spill badly at 64 registers
 
 }  // namespace
 
-int hadi_douglas_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj, bool need_global, HadiPlan* plan) {
+int hadi_douglas_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj, bool need_global, HadiPlan* plan,
+                      bool want_cluster) {
   int max_smem = 0, sms = 0;
   cudaError_t e = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   if (e != cudaSuccess) return (int)e;
@@ -488,6 +633,26 @@ int hadi_douglas_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj
   const VariantInfo* v = variants();
   int pick = -1;
   size_t smem = 0;
+  {
+    // the cluster kernel: global working set, HADI_CLUSTER CTAs of 1024 threads per solve
+    const char* fv = getenv("HADI_FORCE_VARIANT");
+    const bool forced = fv && atoi(fv) == kClusterVariant;
+    if ((want_cluster && need_global && !(fv && !forced)) || forced) {
+      const size_t sm = hadi_smem_layout(m1, m2, ld, n1, n2, pj, false, true).total;
+      if (sm <= (size_t)max_smem && m1 + 1 <= kClusterThreads * HADI_CLUSTER && m2 + 1 < kClusterThreads * HADI_CLUSTER) {
+        e = cudaFuncSetAttribute((const void*)hadi_cluster_kernel<kClusterThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return (int)e;
+        plan->global_state = true;
+        plan->variant = kClusterVariant;
+        plan->threads = kClusterThreads;
+        plan->ctas_per_sm = 1;
+        plan->sm_count = sms;
+        plan->smem_bytes = sm;
+        plan->cluster = HADI_CLUSTER;
+        return 0;
+      }
+    }
+  }
   // development aid: HADI_FORCE_VARIANT=<id> restricts the choice (e.g. 2 = run-time dims, direct loads)
   const char* force = getenv("HADI_FORCE_VARIANT");
   for (int k = 0; k < kNumVariants; ++k) {
@@ -514,6 +679,7 @@ int hadi_douglas_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj
   plan->ctas_per_sm = occ;
   plan->sm_count = sms;
   plan->smem_bytes = smem;
+  plan->cluster = 1;
   return 0;
 }
 
@@ -526,6 +692,9 @@ int hadi_launch_douglas(const HadiLaunch& L, const HadiPlan& plan, int grid_ctas
     break;
     HADI_VARIANTS(X)
 #undef X
+    case kClusterVariant:
+      hadi_cluster_kernel<kClusterThreads><<<grid_ctas, kClusterThreads, plan.smem_bytes, st>>>(L);
+      break;
     default:
       return (int)cudaErrorInvalidValue;
   }

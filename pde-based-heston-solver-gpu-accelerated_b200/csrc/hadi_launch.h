@@ -37,6 +37,7 @@ struct HadiPlan {
   int ctas_per_sm;    // resident CTAs per SM at this shared-memory footprint
   int sm_count;
   size_t smem_bytes;  // dynamic shared memory per CTA
+  int cluster;        // CTAs that share one solve (1, or HADI_CLUSTER in the cluster kernel)
 };
 
 // shared memory layout of the Douglas kernel (offsets in bytes from the dynamic smem base)
@@ -69,7 +70,7 @@ HADI_HD HadiSmemLayout hadi_smem_layout(int m1, int m2, int ld, int n1, int n2, 
 // per-CTA global scratch: fM [m1][pj], fB [m1][2*pj], lambda [m2+1][ld]; the global-state kernel adds
 // U (with halo) and Y, and for Craig-Sneyd Y0, R0, R1, R2 — every array starts on a 128-byte boundary
 struct HadiScratchLayout {
-  size_t fM, fB, lam, U, Y, Y0, R0, R1, R2, total;   // offsets in doubles
+  size_t fM, fB, lam, U, Y, Y0, R0, R1, R2, mail, total;   // offsets in doubles
 };
 HADI_HD HadiScratchLayout hadi_scratch_layout(int m1, int m2, int ld, int pj, bool global_state, bool cs) {
   HadiScratchLayout s;
@@ -87,10 +88,13 @@ HADI_HD HadiScratchLayout hadi_scratch_layout(int m1, int m2, int ld, int pj, bo
   s.R0 = off; if (cs) off += arr; off = (off + 15) & ~size_t(15);
   s.R1 = off; if (cs) off += arr; off = (off + 15) & ~size_t(15);
   s.R2 = off; if (cs) off += arr; off = (off + 15) & ~size_t(15);
+  s.mail = off; off += 16;   // cluster kernel: work-item mailbox and vote word
   s.total = (off + 31) & ~size_t(31);
   return s;
 }
 
 // defined in hadi_kernel.cu; return 0 or a cudaError_t
-int hadi_douglas_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj, bool need_global, HadiPlan* plan);
+#define HADI_CLUSTER 8
+int hadi_douglas_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj, bool need_global, HadiPlan* plan,
+                      bool want_cluster = false);
 int hadi_launch_douglas(const HadiLaunch& L, const HadiPlan& plan, int grid_ctas, void* stream);

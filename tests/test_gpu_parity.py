@@ -344,6 +344,31 @@ def test_large_grid_beyond_shared_memory(hadi, ctx, oracle):
     assert g["prices"][0] == o["price"] and np.array_equal(g["U"][0], o["U"])
 
 
+@pytest.mark.parametrize("variant", ["5", "6"])
+def test_large_grid_one_cta_and_cluster_kernels(hadi, ctx, oracle, monkeypatch, variant):
+    """Grids beyond shared memory run either one CTA per solve (variant 5, TMA-ring factor feed) or one
+    thread-block cluster per solve (variant 6, chosen when there are few items).  Both must reproduce the
+    oracle bit for bit: European Douglas, American Douglas (projection across the cluster) and Craig-Sneyd,
+    and a batch with more items than clusters (work-item mailbox, vote word)."""
+    monkeypatch.setenv("HADI_FORCE_VARIANT", variant)
+    m1, m2, N = 300, 150, 4
+    o = oracle.solve(100.0, N, 1.0 / 100, m1=m1, m2=m2, theta=0.8, want_lambda=False, **BASE)
+    g = solve_gpu(hadi, ctx, [100.0], N, N / 100.0, m1, m2)
+    assert g["prices"][0] == o["price"] and np.array_equal(g["U"][0], o["U"])
+    o = oracle.solve(100.0, N, 1.0 / 100, m1=m1, m2=m2, theta=0.8, style=1, **BASE)
+    g = solve_gpu(hadi, ctx, [100.0], N, N / 100.0, m1, m2, style=1)
+    assert g["prices"][0] == o["price"] and np.array_equal(g["U"][0], o["U"])
+    assert np.array_equal(g["lambda"][0], o["lambda"])
+    o = oracle.solve(100.0, N, 1.0 / 100, m1=m1, m2=m2, theta=0.8, scheme=1, want_lambda=False, **BASE)
+    g = solve_gpu_cs(hadi, ctx, [100.0], N, N / 100.0, m1, m2)
+    assert g["prices"][0] == o["price"] and np.array_equal(g["U"][0], o["U"])
+    strikes = [90.0 + 0.5 * k for k in range(40)]
+    a = solve_gpu(hadi, ctx, strikes, N, N / 100.0, m1, m2)["prices"]
+    monkeypatch.setenv("HADI_FORCE_VARIANT", "5" if variant == "6" else "6")
+    b = solve_gpu(hadi, ctx, strikes, N, N / 100.0, m1, m2)["prices"]
+    assert np.array_equal(a, b)
+
+
 def test_config4_full_size_golden(hadi, ctx):
     """BASELINE config 4 at full size: European call, 400 x 200 x 200.  Golden prices from the reference's
     own code (SURVEY.md 8(c) probe): Craig-Sneyd host solver and device Douglas path."""
