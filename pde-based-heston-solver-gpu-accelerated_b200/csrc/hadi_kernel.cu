@@ -584,8 +584,11 @@ __global__ void __cluster_dims__(HADI_CLUSTER, 1, 1) __launch_bounds__(NT, 1) ha
 // 1:  51 x 26 nodes (the reference's own test / benchmark grid): 256 threads = 5 x 51 (+1), 3 CTAs/SM
 // 2: any grid with m1+1 <= 416 that fits shared memory, run-time dimensions, direct factor loads
 // 3: any grid with m1+1 <= 1024 that fits shared memory, run-time dimensions, one CTA per SM
-// 5: any grid with m1+1 <= 1024: U and Y in L2-resident global scratch, tables in shared memory, TMA ring for
-//    the A1 factors, one CTA per SM (grids beyond shared memory, e.g. 401 x 201; all Craig-Sneyd solves)
+// 5: any grid with m1+1 <= 512: U and Y in L2-resident global scratch, tables in shared memory, TMA ring for
+//    the A1 factors, one CTA of 512 threads (128 registers) per SM (grids beyond shared memory, e.g. 401 x 201;
+//    all Craig-Sneyd solves)
+// 6: the same with 1024 threads (64 registers: the generic phases spill) for m1+1 <= 1024
+// 7: the cluster kernel (hadi_cluster_kernel), chosen by hadi_douglas_plan when there are few items
 // Factor feed of the grid-specialised variants, measured on B200 (round 1): at 101x51 plain loads (2.68 ms for
 // config 2) beat the TMA ring (2.78 ms: mbarrier try_wait costs ~90 cycles per chunk on the dependent chain),
 // per-thread cp.async stages (2.97 ms) and L1 prefetches (2.87 ms); at 51x26 the L1 prefetch wins.
@@ -601,7 +604,8 @@ __global__ void __cluster_dims__(HADI_CLUSTER, 1, 1) __launch_bounds__(NT, 1) ha
   X(2, 416, 2, 0, 0, 0, false)          \
   X(3, 1024, 1, 0, 0, 0, false)         \
   X(4, 320, 2, 100, 50, 4, false)       \
-  X(5, 1024, 1, 0, 0, 1, true)
+  X(5, 512, 1, 0, 0, 1, true)           \
+  X(6, 1024, 1, 0, 0, 1, true)
 
 struct VariantInfo {
   int threads, m1, m2;
@@ -617,8 +621,8 @@ const VariantInfo* variants() {
   };
   return v;
 }
-constexpr int kNumVariants = 6;
-constexpr int kClusterVariant = 6;   // hadi_cluster_kernel: one solve per thread-block cluster
+constexpr int kNumVariants = 7;
+constexpr int kClusterVariant = 7;   // hadi_cluster_kernel: one solve per thread-block cluster
 constexpr int kClusterThreads = 256; // few threads, many registers: the generic phases spill badly at 64 registers
 
 }  // namespace

@@ -344,10 +344,10 @@ def test_large_grid_beyond_shared_memory(hadi, ctx, oracle):
     assert g["prices"][0] == o["price"] and np.array_equal(g["U"][0], o["U"])
 
 
-@pytest.mark.parametrize("variant", ["5", "6"])
+@pytest.mark.parametrize("variant", ["5", "7"])
 def test_large_grid_one_cta_and_cluster_kernels(hadi, ctx, oracle, monkeypatch, variant):
     """Grids beyond shared memory run either one CTA per solve (variant 5, TMA-ring factor feed) or one
-    thread-block cluster per solve (variant 6, chosen when there are few items).  Both must reproduce the
+    thread-block cluster per solve (variant 7, chosen when there are few items).  Both must reproduce the
     oracle bit for bit: European Douglas, American Douglas (projection across the cluster) and Craig-Sneyd,
     and a batch with more items than clusters (work-item mailbox, vote word)."""
     monkeypatch.setenv("HADI_FORCE_VARIANT", variant)
@@ -364,7 +364,7 @@ def test_large_grid_one_cta_and_cluster_kernels(hadi, ctx, oracle, monkeypatch, 
     assert g["prices"][0] == o["price"] and np.array_equal(g["U"][0], o["U"])
     strikes = [90.0 + 0.5 * k for k in range(40)]
     a = solve_gpu(hadi, ctx, strikes, N, N / 100.0, m1, m2)["prices"]
-    monkeypatch.setenv("HADI_FORCE_VARIANT", "5" if variant == "6" else "6")
+    monkeypatch.setenv("HADI_FORCE_VARIANT", "5" if variant == "7" else "7")
     b = solve_gpu(hadi, ctx, strikes, N, N / 100.0, m1, m2)["prices"]
     assert np.array_equal(a, b)
 

@@ -5,7 +5,7 @@ hadi = ge.load_hadi()
 BASE = dict(S0=100.0, V0=0.04, r_d=0.025, r_f=0.0, rho=-0.9, sigma=0.3, kappa=1.5, eta=0.04)
 ctx = hadi.Context(0)
 mdl = hadi.make_model(**BASE)
-for var in ("5", "6"):
+for var in ("6", "5", "7"):
     os.environ["HADI_FORCE_VARIANT"] = var
     for scheme, name in ((hadi.CRAIG_SNEYD, "CS"), (hadi.DOUGLAS, "DO")):
         for N in (20, 200):
