@@ -347,9 +347,14 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
+        traffic = None
+        try:   # DRAM bytes of one launch of this kernel from the committed ncu --set full capture
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
         roofline = {"bound": "fp64", "achieved": achieved, "peak": unfused, "unit": "TFLOP/s",
                     "frac": achieved / unfused,
-                    "traffic": None,
+                    "traffic": traffic,
                     "note": "FP64-pipe bound, SMEM-resident (not hbm/tensor): peak = un-fused DMUL+DADD issue rate "
                             "measured live by hadi_measure_fp64 (parity forbids FMA; DFMA rate %.1f TFLOP/s); "
                             "algorithmic flops = %d options x %d steps x %d nodes x %d; algorithmic HBM bytes per "
