@@ -193,6 +193,33 @@ int hadi_grid(int m1, int m2, double K, double S0, double V0, double* s, double*
 /* BlackScholes::call_price (src/bs.hpp:44-55) */
 double hadi_bs_call(double S, double K, double r, double vol, double T);
 
+/* ---- callers either side of the calibration driver (host only) ----- */
+/* BlackScholes::call_vega, CP = 1 (src/bs.hpp:124-127) */
+double hadi_bs_vega(double S, double K, double r, double vol, double T);
+/* BlackScholes::reverse_BS_dic (src/bs.hpp:131-160): bisection on [a, b] until |C - target| <= epsilon */
+double hadi_bs_implied_vol_bisect(double S, double K, double r, double T, double target, double epsilon,
+                                  double a, double b);
+/* BlackScholes::reverse_BS (src/bs.hpp:164-192): Newton from v0, bisection on [0.001, 1] when vega < 1e-10 */
+double hadi_bs_implied_vol(double S, double K, double r, double T, double v0, double target, double epsilon);
+/* spot net of the discounted dividends paid before T (src/bs.hpp:91-102, src/heston_calibration.cpp:1500-1511) */
+double hadi_dividend_adjusted_spot(double S0, double T, double r_d, int num_dividends, const double* dates,
+                                   const double* amounts, const double* percentages);
+/* BlackScholes::generate_market_data{,_with_dividends} (src/bs.hpp:58-112) per calibration point;
+ * prices[global_index]; num_dividends = 0 selects the plain generator */
+int hadi_market_prices(double S0, double r_d, double market_vol, int n, const hadi_point* points,
+                       int num_dividends, const double* dates, const double* amounts, const double* percentages,
+                       double* prices);
+/* implied vols of market and fitted prices and their absolute difference (src/heston_calibration.cpp:441-460,
+ * 2890-2910); arrays indexed by global_index, any output may be NULL */
+int hadi_implied_vols(double spot, double r_d, int n, const hadi_point* points, const double* market,
+                      const double* fitted, double epsilon, double* market_iv, double* fitted_iv, double* iv_diff);
+/* calibration report: format 0 = fitted_heston_vs_market.csv (src/heston_calibration.cpp:467-508),
+ * format 1 = fitted_heston_vs_market_multi_maturity.csv (:2857-2921) */
+int hadi_write_calibration_csv(const char* path, int format, double spot, double r_d, int num_maturities,
+                               int num_strikes, const hadi_point* points, const double* market,
+                               const double* fitted, const hadi_model* initial, const hadi_lm_result* result,
+                               double total_time_s, double iv_epsilon);
+
 #ifdef __cplusplus
 }
 #endif

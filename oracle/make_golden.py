@@ -33,9 +33,40 @@ def digest(a):
     return hashlib.sha256(a.tobytes()).hexdigest()
 
 
+def market_fixtures(R):
+    """Synthetic market, dividend-adjusted market and implied-vol inversion (src/bs.hpp:58-192)."""
+    strikes = [90.0 + 2.5 * i for i in range(9)]
+    cases = []
+    for T in (0.5, 1.0, 2.75):
+        plain = R.market(100.0, T, 0.025, strikes)
+        div = R.market(100.0, T, 0.025, strikes, DIVS)
+        cases.append(dict(S0=100.0, T=T, r_d=0.025, strikes=strikes, plain=[repr(float(x)) for x in plain],
+                          dividends=[repr(float(x)) for x in div]))
+    iv = []
+    for (S, K, r, T, target) in [(100.0, 100.0, 0.025, 1.0, 9.0), (100.0, 90.0, 0.025, 0.5, 12.5),
+                                 (100.0, 110.0, 0.025, 2.75, 11.0), (97.1, 100.0, 0.025, 1.0, 6.4),
+                                 (100.0, 100.0, 0.025, 1.0, float(R.bs_call(100.0, 100.0, 0.025, 0.2, 1.0)))]:
+        for eps in (0.01, 1e-8):
+            iv.append(dict(S=S, K=K, r=r, T=T, target=repr(target), eps=eps,
+                           newton=repr(float(R.reverse_bs(S, K, r, T, 0.5, target, eps))),
+                           bisect=repr(float(R.reverse_bs_dic(S, K, r, T, target, eps, 0.001, 1.0))),
+                           vega=repr(float(R.bs_vega(S, K, r, 0.2, T)))))
+    # a deep in-the-money target at a tiny maturity: vega < 1e-10 at the first Newton step -> bisection fallback
+    S, K, r, T, target, eps = 100.0, 20.0, 0.025, 0.001, 80.2, 1e-6
+    iv.append(dict(S=S, K=K, r=r, T=T, target=repr(target), eps=eps, fallback=True,
+                   newton=repr(float(R.reverse_bs(S, K, r, T, 0.5, target, eps))),
+                   bisect=repr(float(R.reverse_bs_dic(S, K, r, T, target, eps, 0.001, 1.0))),
+                   vega=repr(float(R.bs_vega(S, K, r, 0.5, T)))))
+    json.dump(dict(divs=DIVS, market=cases, implied_vol=iv), open(os.path.join(OUT, "market.json"), "w"), indent=0)
+
+
 def main():
     R = RefLib()
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "market":
+        market_fixtures(R)
+        return
+    market_fixtures(R)
 
     # ---- grids (src/grid.cpp:16-96)
     grids = []

@@ -18,6 +18,8 @@
 #include <Kokkos_Core.hpp>
 
 #include <cstdio>
+#include <iostream>
+#include <sstream>
 #include <cstring>
 #include <vector>
 
@@ -345,6 +347,45 @@ int hadi_ref_solve5(const double* A, const double* b, double* x) {
 
 double hadi_ref_bs_call(double S, double K, double r, double vol, double T) {
   return BlackScholes::call_price(1, S, K, r, vol, T);
+}
+
+// Implied-volatility helpers and the synthetic market generators (src/bs.hpp:58-192).  The reference prints
+// from inside them; std::cout is silenced for the duration of the call.
+namespace {
+struct QuietCout {
+  std::streambuf* old;
+  std::ostringstream sink;
+  QuietCout() : old(std::cout.rdbuf(sink.rdbuf())) {}
+  ~QuietCout() { std::cout.rdbuf(old); }
+};
+}  // namespace
+double hadi_ref_bs_vega(double S, double K, double r, double vol, double T) {
+  return BlackScholes::call_vega(1, S, K, r, vol, T);
+}
+double hadi_ref_reverse_bs(double S, double K, double r, double T, double v0, double target, double eps) {
+  QuietCout q;
+  return BlackScholes::reverse_BS(1, S, K, r, T, v0, target, eps);
+}
+double hadi_ref_reverse_bs_dic(double S, double K, double r, double T, double target, double eps, double a,
+                               double b) {
+  QuietCout q;
+  return BlackScholes::reverse_BS_dic(1, S, K, r, T, target, eps, a, b);
+}
+// nd = 0: generate_market_data, else generate_market_data_with_dividends; prices[n] for strikes[n] at maturity T
+int hadi_ref_market(double S0, double T, double r_d, int n, const double* strikes, int nd, const double* dates,
+                    const double* amounts, const double* pcts, double* prices) {
+  QuietCout q;
+  std::vector<double> k(strikes, strikes + n);
+  Kokkos::View<double*> mp("market", n);
+  auto h = Kokkos::create_mirror_view(mp);
+  if (nd == 0) {
+    BlackScholes::generate_market_data(S0, T, r_d, k, h);
+  } else {
+    std::vector<double> dd(dates, dates + nd), da(amounts, amounts + nd), dp(pcts, pcts + nd);
+    BlackScholes::generate_market_data_with_dividends(S0, T, r_d, k, dd, da, dp, h);
+  }
+  for (int i = 0; i < n; ++i) prices[i] = h(i);
+  return 0;
 }
 
 // Host-driven schemes of src/solver.hpp on the reference's host matrix classes

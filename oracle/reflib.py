@@ -114,6 +114,35 @@ class RefLib:
     def bs_call(self, S, K, r, vol, T):
         return self.lib.hadi_ref_bs_call(S, K, r, vol, T)
 
+    def bs_vega(self, S, K, r, vol, T):
+        self.lib.hadi_ref_bs_vega.restype = C.c_double
+        self.lib.hadi_ref_bs_vega.argtypes = [C.c_double] * 5
+        return self.lib.hadi_ref_bs_vega(S, K, r, vol, T)
+
+    def reverse_bs(self, S, K, r, T, v0, target, eps):
+        self.lib.hadi_ref_reverse_bs.restype = C.c_double
+        self.lib.hadi_ref_reverse_bs.argtypes = [C.c_double] * 7
+        return self.lib.hadi_ref_reverse_bs(S, K, r, T, v0, target, eps)
+
+    def reverse_bs_dic(self, S, K, r, T, target, eps, a, b):
+        self.lib.hadi_ref_reverse_bs_dic.restype = C.c_double
+        self.lib.hadi_ref_reverse_bs_dic.argtypes = [C.c_double] * 8
+        return self.lib.hadi_ref_reverse_bs_dic(S, K, r, T, target, eps, a, b)
+
+    def market(self, S0, T, r_d, strikes, divs=None):
+        k = np.ascontiguousarray(strikes, dtype=np.float64)
+        out = np.zeros(k.size)
+        if divs:
+            dd, da, dp = (np.ascontiguousarray(x, dtype=np.float64) for x in divs)
+            nd = dd.size
+        else:
+            dd = da = dp = None
+            nd = 0
+        self.lib.hadi_ref_market.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, _dp, C.c_int, _dp, _dp,
+                                             _dp, _dp]
+        self.lib.hadi_ref_market(S0, T, r_d, k.size, _d(k), nd, _d(dd), _d(da), _d(dp), _d(out))
+        return out
+
     def host_scheme(self, scheme, *, K, S0, V0, T, r_d, r_f, rho, sigma, kappa, eta, m1, m2, N, theta,
                     want_U=False):
         price = C.c_double(0.0)

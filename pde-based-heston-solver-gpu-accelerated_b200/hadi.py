@@ -29,7 +29,8 @@ EXPORTS = [
     "hadi_batch_launch", "hadi_batch_values_dev", "hadi_batch_fetch", "hadi_batch_elapsed_ms",
     "hadi_batch_destroy", "hadi_jacobian_assemble", "hadi_partition", "hadi_item_costs", "hadi_solve5",
     "hadi_lm_update", "hadi_calibrate", "hadi_grid", "hadi_bs_call", "hadi_transfer_bytes", "hadi_measure_fp64",
-    "hadi_batch_phase_cycles",
+    "hadi_batch_phase_cycles", "hadi_bs_vega", "hadi_bs_implied_vol", "hadi_bs_implied_vol_bisect",
+    "hadi_dividend_adjusted_spot", "hadi_market_prices", "hadi_implied_vols", "hadi_write_calibration_csv",
 ]
 
 
@@ -119,6 +120,21 @@ def lib():
         L.hadi_transfer_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
         L.hadi_measure_fp64.argtypes = [C.c_int] + [C.POINTER(C.c_double)] * 3
         L.hadi_batch_phase_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
+        L.hadi_bs_vega.argtypes = [C.c_double] * 5
+        L.hadi_bs_vega.restype = C.c_double
+        L.hadi_bs_implied_vol.argtypes = [C.c_double] * 7
+        L.hadi_bs_implied_vol.restype = C.c_double
+        L.hadi_bs_implied_vol_bisect.argtypes = [C.c_double] * 8
+        L.hadi_bs_implied_vol_bisect.restype = C.c_double
+        L.hadi_dividend_adjusted_spot.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, _dp, _dp, _dp]
+        L.hadi_dividend_adjusted_spot.restype = C.c_double
+        L.hadi_market_prices.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(Point), C.c_int,
+                                         _dp, _dp, _dp, _dp]
+        L.hadi_implied_vols.argtypes = [C.c_double, C.c_double, C.c_int, C.POINTER(Point), _dp, _dp, C.c_double,
+                                        _dp, _dp, _dp]
+        L.hadi_write_calibration_csv.argtypes = [C.c_char_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
+                                                 C.POINTER(Point), _dp, _dp, C.POINTER(Model), C.POINTER(LmResult),
+                                                 C.c_double, C.c_double]
         _lib = L
     return _lib
 
@@ -181,6 +197,67 @@ def measure_fp64(device=0):
 
 def bs_call(S, K, r, vol, T):
     return lib().hadi_bs_call(S, K, r, vol, T)
+
+
+def bs_vega(S, K, r, vol, T):
+    return lib().hadi_bs_vega(S, K, r, vol, T)
+
+
+def bs_implied_vol(S, K, r, T, v0, target, eps):
+    return lib().hadi_bs_implied_vol(S, K, r, T, v0, target, eps)
+
+
+def bs_implied_vol_bisect(S, K, r, T, target, eps, a, b):
+    return lib().hadi_bs_implied_vol_bisect(S, K, r, T, target, eps, a, b)
+
+
+def _divs(divs):
+    if divs is None or len(divs[0]) == 0:
+        return 0, None, None, None, []
+    arrs = [np.ascontiguousarray(x, dtype=np.float64) for x in divs]
+    return arrs[0].size, _d(arrs[0]), _d(arrs[1]), _d(arrs[2]), arrs
+
+
+def dividend_adjusted_spot(S0, T, r_d, divs):
+    nd, a, b, c, keep = _divs(divs)
+    return lib().hadi_dividend_adjusted_spot(S0, T, r_d, nd, a, b, c)
+
+
+def market_prices(S0, r_d, vol, pts, n, divs=None):
+    nd, a, b, c, keep = _divs(divs)
+    out = np.zeros(max(n, 1))
+    rc = lib().hadi_market_prices(S0, r_d, vol, n, pts, nd, a, b, c, _d(out))
+    if rc != OK:
+        raise HadiError(rc)
+    return out[:n]
+
+
+def implied_vols(spot, r_d, pts, n, market, fitted, eps=0.01):
+    market = np.ascontiguousarray(market, dtype=np.float64)
+    fitted = np.ascontiguousarray(fitted, dtype=np.float64)
+    miv, fiv, dif = np.zeros(max(n, 1)), np.zeros(max(n, 1)), np.zeros(max(n, 1))
+    rc = lib().hadi_implied_vols(spot, r_d, n, pts, _d(market), _d(fitted), eps, _d(miv), _d(fiv), _d(dif))
+    if rc != OK:
+        raise HadiError(rc)
+    return miv[:n], fiv[:n], dif[:n]
+
+
+def write_calibration_csv(path, fmt, spot, r_d, n_maturities, n_strikes, pts, market, fitted, initial, result,
+                          total_time_s, iv_eps=0.01):
+    """`result` is the dict Context.calibrate returns."""
+    market = np.ascontiguousarray(market, dtype=np.float64)
+    fitted = np.ascontiguousarray(fitted, dtype=np.float64)
+    res = LmResult()
+    for k in range(5):
+        res.params[k] = result["params"][k]
+    res.final_error = result["final_error"]
+    res.iterations = result["iterations"]
+    res.pde_solves = result["pde_solves"]
+    rc = lib().hadi_write_calibration_csv(os.fsencode(path), fmt, spot, r_d, n_maturities, n_strikes, pts,
+                                          _d(market), _d(fitted), C.byref(initial), C.byref(res), total_time_s,
+                                          iv_eps)
+    if rc != OK:
+        raise HadiError(rc)
 
 
 def solve5(A, b):

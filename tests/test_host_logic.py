@@ -82,3 +82,72 @@ def test_bad_arguments_are_rejected_without_a_gpu(hadi):
     b, e = ctypes.c_int(), ctypes.c_int()
     assert L.hadi_partition(5, None, 0, 0, ctypes.byref(b), ctypes.byref(e)) == hadi.ERR_ARG
     assert L.hadi_price_batch(None, None, None, 0, None, None, None, None) == hadi.ERR_ARG
+
+
+def test_market_generators_and_implied_vol(hadi):
+    """synthetic market (plain / dividend-adjusted spot), vega, Newton and bisection
+    implied-vol inversion, bit-equal to the reference's BlackScholes class (src/bs.hpp:58-192)."""
+    G = golden("market.json")
+    for c in G["market"]:
+        n = len(c["strikes"])
+        pts, _ = hadi.make_points(c["strikes"], c["T"], 20)
+        plain = hadi.market_prices(c["S0"], c["r_d"], 0.2, pts, n)
+        div = hadi.market_prices(c["S0"], c["r_d"], 0.2, pts, n, divs=G["divs"])
+        assert [repr(float(x)) for x in plain] == c["plain"]
+        assert [repr(float(x)) for x in div] == c["dividends"]
+        # the dividend-adjusted spot is what the generator priced at
+        sa = hadi.dividend_adjusted_spot(c["S0"], c["T"], c["r_d"], G["divs"])
+        assert repr(hadi.bs_call(sa, c["strikes"][0], c["r_d"], 0.2, c["T"])) == c["dividends"][0]
+    for c in G["implied_vol"]:
+        t = float(c["target"])
+        assert repr(hadi.bs_implied_vol(c["S"], c["K"], c["r"], c["T"], 0.5, t, c["eps"])) == c["newton"]
+        assert repr(hadi.bs_implied_vol_bisect(c["S"], c["K"], c["r"], c["T"], t, c["eps"], 0.001, 1.0)) == c["bisect"]
+        vol = 0.5 if c.get("fallback") else 0.2
+        assert repr(hadi.bs_vega(c["S"], c["K"], c["r"], vol, c["T"])) == c["vega"]
+
+
+def test_market_helpers_against_the_reference(hadi, reflib):
+    rng = np.random.default_rng(11)
+    for _ in range(40):
+        S, K = 100.0 * (1 + 0.1 * rng.normal()), 100.0 * (1 + 0.2 * rng.normal())
+        T, vol = float(rng.uniform(0.1, 3.0)), float(rng.uniform(0.08, 0.6))
+        target = hadi.bs_call(S, K, 0.025, vol, T)
+        assert hadi.bs_vega(S, K, 0.025, vol, T) == reflib.bs_vega(S, K, 0.025, vol, T)
+        assert hadi.bs_implied_vol(S, K, 0.025, T, 0.5, target, 0.01) == reflib.reverse_bs(S, K, 0.025, T, 0.5, target, 0.01)
+        assert (hadi.bs_implied_vol_bisect(S, K, 0.025, T, target, 1e-9, 0.001, 1.0)
+                == reflib.reverse_bs_dic(S, K, 0.025, T, target, 1e-9, 0.001, 1.0))
+
+
+def test_calibration_report_writer(hadi, tmp_path):
+    """The CSV the reference's LM drivers export (src/heston_calibration.cpp:467-508, 2857-2921): same header
+    fields, same columns, doubles streamed at the default precision."""
+    strikes = [95.0 + s for s in range(4)]
+    mats = [1.0, 1.5]
+    K = [k for _ in mats for k in strikes]
+    T = [t for t in mats for _ in strikes]
+    pts, n = hadi.make_points(K, T, [max(20, int(20 * t)) for t in T])
+    market = hadi.market_prices(100.0, 0.025, 0.2, pts, n)
+    fitted = market + 0.05
+    initial = hadi.make_model(100.0, 0.04, 0.025, 0.0, 1.5, 0.04, 0.3, -0.9)
+    res = dict(params=[4.5, 0.04, 0.1, -0.11, 0.042], final_error=1.25, iterations=3, pde_solves=160)
+    p1 = str(tmp_path / "multi.csv")
+    hadi.write_calibration_csv(p1, 1, 100.0, 0.025, len(mats), len(strikes), pts, market, fitted, initial, res, 0.5)
+    lines = open(p1).read().splitlines()
+    assert lines[0] == ("# Calibration with 2 maturities, 4 strikes per maturity, Time=0.5 s, FinalError=1.25, "
+                        "IterationCount=3, TotalPdeSolves=160, init_kappa=1.5, init_eta=0.04, init_sigma=0.3, "
+                        "init_rho=-0.9, init_v0=0.04, kappa=4.5, eta=0.04, sigma=0.1, rho=-0.11, v0=0.042")
+    assert lines[1] == "Maturity,Strike,MarketPrice,FittedPrice,MarketIV,FittedIV,IVDifference"
+    assert len(lines) == 2 + n
+    miv, fiv, dif = hadi.implied_vols(100.0, 0.025, pts, n, market, fitted, 0.01)
+    row = lines[2 + 5].split(",")
+    assert row[0] == "1.5" and row[1] == "96"
+    assert row[2] == "%g" % market[5] and row[3] == "%g" % fitted[5]
+    assert row[4] == "%g" % miv[5] and row[5] == "%g" % fiv[5] and row[6] == "%g" % dif[5]
+    # single-maturity format
+    pts1, n1 = hadi.make_points(strikes, 1.0, 20)
+    p0 = str(tmp_path / "single.csv")
+    hadi.write_calibration_csv(p0, 0, 100.0, 0.025, 1, n1, pts1, market[:n1], fitted[:n1], initial, res, 0.25)
+    lines = open(p0).read().splitlines()
+    assert lines[0].startswith("# 4 options, Time=0.25 s, FinalError=1.25, iterationCount=3, TotalPdeSolves=160, init_kappa=1.5")
+    assert lines[1] == "Strike,MarketPrice,FittedPrice,IVDifference" and len(lines) == 2 + n1
+    assert lines[2].split(",")[0] == "95"
