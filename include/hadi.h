@@ -130,19 +130,39 @@ int hadi_jacobian_batch(hadi_ctx* ctx, const hadi_model* model, const hadi_numer
 
 /* ---- prepared batches: descriptors + grids resident in HBM, launch / fetch separately --------- */
 #define HADI_MODE_PRICE 0
-#define HADI_MODE_JACOBIAN 1
+#define HADI_MODE_JACOBIAN 1          /* the reference's Jacobian: forward differences, 6 solves per option */
+/* opt-in alternatives; they change the numbers, so parity with the reference's
+ * LM trajectory holds for HADI_MODE_JACOBIAN only:
+ *   INTERP   the V0 column from the base solve, interpolated linearly in v between the rows bracketing
+ *            V0 + eps (the reference's prototype, src/device_solver.cpp:1725-1829): 5 solves per option,
+ *            item index = option*5 + {base, kappa, eta, sigma, rho}, THREE values per item
+ *            {price, U(S0, v_lower), U(S0, v_upper)}
+ *   CENTRAL  (p(+eps) - p(-eps)) / (2 eps): 11 solves per option, item index = option*11 +
+ *            {base, +kappa, +eta, +sigma, +rho, +v0, -kappa, -eta, -sigma, -rho, -v0} */
+#define HADI_MODE_JACOBIAN_INTERP 2
+#define HADI_MODE_JACOBIAN_CENTRAL 3
+typedef struct {
+  int mode;        /* HADI_MODE_JACOBIAN | _INTERP | _CENTRAL */
+  double eps[5];   /* bump per parameter (kappa, eta, sigma, rho, v0); the reference uses 1e-6 for all */
+} hadi_jacobian_options;
 /* Work items are options (PRICE) or option x {base, kappa, eta, sigma, rho, v0} (JACOBIAN), item
  * index = option*6 + column.  [item_begin, item_end) selects the slice this context solves
  * (multi-GPU sharding); pass 0, -1 for everything. */
 int hadi_batch_create(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
                       const hadi_point* points, int mode, double eps, int item_begin, int item_end,
                       hadi_batch** out);
+/* as hadi_batch_create with one bump per parameter (eps5[5]) */
+int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
+                         const hadi_point* points, int mode, const double* eps5, int item_begin, int item_end,
+                         hadi_batch** out);
 int hadi_batch_num_items(const hadi_batch* b);
+/* values each item publishes: 1, or 3 in HADI_MODE_JACOBIAN_INTERP */
+int hadi_batch_values_per_item(const hadi_batch* b);
 /* enqueue the solve on the context's stream (asynchronous) */
 int hadi_batch_launch(hadi_batch* b);
 /* device pointer to the item values (one double per item of the slice, slice order) */
 double* hadi_batch_values_dev(hadi_batch* b);
-/* wait and copy the slice's item values to the host (values[item_end-item_begin]) */
+/* wait and copy the slice's item values to the host (values[(item_end-item_begin) * values_per_item]) */
 int hadi_batch_fetch(hadi_batch* b, double* values);
 /* elapsed device time of the last launch in ms (CUDA events on the context's stream) */
 int hadi_batch_elapsed_ms(hadi_batch* b, float* ms);
@@ -155,9 +175,19 @@ void hadi_batch_destroy(hadi_batch* b);
  * (src/jacobian_computation.cpp:330,361). */
 int hadi_jacobian_assemble(int n, const double* item_values, double eps, double* J, double* base_prices);
 
+/* Jacobian rows from the item values of any Jacobian mode (layouts above); v0_weight from hadi_jacobian_v0_weight */
+int hadi_jacobian_assemble_ex(int n, int mode, const double* item_values, const double* eps5, double v0_weight,
+                              double* J, double* base_prices);
+/* rows of the base v-grid bracketing V0 + eps_v0 and the linear weight (src/device_solver.cpp:1735-1754) */
+int hadi_jacobian_v0_weight(int m2, double V0, double eps_v0, int* lower, int* upper, double* weight);
+/* hadi_jacobian_batch with the Jacobian taken as `opt` says */
+int hadi_jacobian_batch_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
+                           const hadi_point* points, const hadi_jacobian_options* opt, double* J,
+                           double* base_prices);
+
 /* Static block partition of item costs over `world` ranks (contiguous, balanced by cost). */
 int hadi_partition(int n_items, const int* costs, int world, int rank, int* begin, int* end);
-/* cost (N*P) of each item of a would-be batch, for hadi_partition; costs[n] or costs[6n] */
+/* cost (N*P) of each item of a would-be batch, for hadi_partition; costs[n * items per option] */
 int hadi_item_costs(const hadi_numerics* num, int n, const hadi_point* points, int mode, int* costs);
 
 /* ---- Levenberg-Marquardt ---------------------------------------------------------------------- */
@@ -180,6 +210,11 @@ typedef struct {
 int hadi_calibrate(hadi_ctx* ctx, const hadi_model* initial, const hadi_numerics* num, int n,
                    const hadi_point* points, const double* market_prices, const hadi_lm_options* opt,
                    const hadi_comm* comm, hadi_lm_result* result);
+
+/* hadi_calibrate with the Jacobian taken as `jopt` says (opt->eps is ignored) */
+int hadi_calibrate_ex(hadi_ctx* ctx, const hadi_model* initial, const hadi_numerics* num, int n,
+                      const hadi_point* points, const double* market_prices, const hadi_lm_options* opt,
+                      const hadi_jacobian_options* jopt, const hadi_comm* comm, hadi_lm_result* result);
 
 /* ---- measurement ------------------------------------------------------------------------------ */
 /* FP64 issue-rate micro-benchmark on `device` (CUDA events): un-fused DMUL+DADD rate and DFMA rate in

@@ -53,6 +53,7 @@ struct hadi_ctx {
 struct hadi_batch {
   hadi_ctx* ctx = nullptr;
   int n_items = 0;
+  int stride = 1;  // values per item (3 in HADI_MODE_JACOBIAN_INTERP)
   int m1 = 0, m2 = 0;
   HadiLaunch L{};
   HadiPlan plan{};
@@ -187,7 +188,32 @@ bool valid_numerics(const hadi_numerics* num) {
   return true;
 }
 
-int n_columns(int mode) { return mode == HADI_MODE_JACOBIAN ? 6 : 1; }
+// work items per option: base + one per bumped parameter
+int n_columns(int mode) {
+  switch (mode) {
+    case HADI_MODE_JACOBIAN: return 6;           // base, kappa, eta, sigma, rho, v0        (forward differences)
+    case HADI_MODE_JACOBIAN_INTERP: return 5;    // base, kappa, eta, sigma, rho            (v0 by interpolation)
+    case HADI_MODE_JACOBIAN_CENTRAL: return 11;  // base, +5 bumps, -5 bumps                (central differences)
+    default: return 1;
+  }
+}
+bool valid_mode(int mode) {
+  return mode == HADI_MODE_PRICE || mode == HADI_MODE_JACOBIAN || mode == HADI_MODE_JACOBIAN_INTERP ||
+         mode == HADI_MODE_JACOBIAN_CENTRAL;
+}
+// The v-rows bracketing V0 + eps on the base v-grid and the interpolation weight
+// (src/device_solver.cpp:1735-1754: first i with v_i <= V0+eps <= v_{i+1}; all zero when there is none).
+void v0_bracket(const double* v, int m2, double v0_pert, int* lo, int* hi, double* weight) {
+  *lo = 0; *hi = 0; *weight = 0.0;
+  for (int i = 0; i < m2; ++i) {
+    if (v[i] <= v0_pert && v0_pert <= v[i + 1]) {
+      *lo = i;
+      *hi = i + 1;
+      *weight = (v0_pert - v[i]) / (v[i + 1] - v[i]);
+      break;
+    }
+  }
+}
 
 }  // namespace
 
@@ -301,14 +327,65 @@ int hadi_jacobian_assemble(int n, const double* v, double eps, double* J, double
   return HADI_OK;
 }
 
+int hadi_jacobian_v0_weight(int m2, double V0, double eps_v0, int* lower, int* upper, double* weight) {
+  if (m2 < 1 || !lower || !upper || !weight) return HADI_ERR_ARG;
+  std::vector<double> v((size_t)m2 + 1);
+  v_grid(nullptr, m2, V0, v.data());
+  v0_bracket(v.data(), m2, V0 + eps_v0, lower, upper, weight);
+  return HADI_OK;
+}
+
+// Jacobian rows from the item values of any Jacobian mode (layouts: include/hadi.h).
+int hadi_jacobian_assemble_ex(int n, int mode, const double* v, const double* eps5, double v0_weight, double* J,
+                              double* base) {
+  if (n < 0 || !v || !eps5 || !J || !base) return HADI_ERR_ARG;
+  if (mode == HADI_MODE_JACOBIAN) {
+    // src/jacobian_computation.cpp:330,361
+    for (int k = 0; k < n; ++k) {
+      const double b = v[6 * k];
+      base[k] = b;
+      for (int c = 0; c < 5; ++c) J[5 * k + c] = (v[6 * k + 1 + c] - b) / eps5[c];
+    }
+  } else if (mode == HADI_MODE_JACOBIAN_INTERP) {
+    // src/device_solver.cpp:1806-1818: the V0 column from the base solve, interpolated linearly in v
+    for (int k = 0; k < n; ++k) {
+      const double* o = v + (size_t)15 * k;   // 5 items x {price, U(S0, v_lower), U(S0, v_upper)}
+      const double b = o[0];
+      base[k] = b;
+      for (int c = 0; c < 4; ++c) J[5 * k + c] = (o[3 * (1 + c)] - b) / eps5[c];
+      const double price_lower = o[1], price_upper = o[2];
+      const double pert_price = price_lower + v0_weight * (price_upper - price_lower);
+      J[5 * k + 4] = (pert_price - b) / eps5[4];
+    }
+  } else if (mode == HADI_MODE_JACOBIAN_CENTRAL) {
+    for (int k = 0; k < n; ++k) {
+      const double* o = v + (size_t)11 * k;
+      base[k] = o[0];
+      for (int c = 0; c < 5; ++c) J[5 * k + c] = (o[1 + c] - o[6 + c]) / (2.0 * eps5[c]);
+    }
+  } else {
+    return HADI_ERR_ARG;
+  }
+  return HADI_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 int hadi_batch_create(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
                       const hadi_point* points, int mode, double eps, int item_begin, int item_end,
                       hadi_batch** out) {
+  const double eps5[5] = {eps, eps, eps, eps, eps};
+  return hadi_batch_create_ex(ctx, model, num, n, points, mode, eps5, item_begin, item_end, out);
+}
+
+int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
+                         const hadi_point* points, int mode, const double* eps5, int item_begin, int item_end,
+                         hadi_batch** out) {
   if (!ctx || !out) return HADI_ERR_ARG;
   *out = nullptr;
-  if (!model || !valid_numerics(num) || n < 0 || (n > 0 && !points)) return fail(ctx, HADI_ERR_ARG, "bad argument");
-  if (mode != HADI_MODE_PRICE && mode != HADI_MODE_JACOBIAN) return fail(ctx, HADI_ERR_ARG, "bad mode");
+  if (!model || !valid_numerics(num) || n < 0 || (n > 0 && !points) || !eps5) return fail(ctx, HADI_ERR_ARG, "bad argument");
+  if (!valid_mode(mode)) return fail(ctx, HADI_ERR_ARG, "bad mode");
+  if (mode == HADI_MODE_JACOBIAN_CENTRAL && !(model->V0 - eps5[4] > 0.0))
+    return fail(ctx, HADI_ERR_ARG, "central differences need V0 - eps > 0");
   if (num->scheme != HADI_DOUGLAS && num->scheme != HADI_CRAIG_SNEYD) return fail(ctx, HADI_ERR_ARG, "unknown scheme");
   // the reference defines Craig-Sneyd for European options without dividends only (src/solver.hpp:781)
   if (num->scheme == HADI_CRAIG_SNEYD && (num->style != HADI_EUROPEAN || num->num_dividends > 0))
@@ -354,15 +431,23 @@ int hadi_batch_create(hadi_ctx* ctx, const hadi_model* model, const hadi_numeric
   std::vector<double> s_pool, v_pool, e_pool;
   std::map<std::pair<uint64_t, uint64_t>, int> s_index;       // (K, S0) -> offset
   std::map<std::pair<uint64_t, int>, int> e_index;            // (dt, N) -> offset
-  // two v-grids at most: V0 and V0 + eps (src/jacobian_computation.cpp:339)
-  v_pool.resize((size_t)2 * (m2 + 1));
+  // three v-grids at most: V0, V0 + eps (src/jacobian_computation.cpp:339) and, for central differences, V0 - eps
+  v_pool.resize((size_t)3 * (m2 + 1));
   v_grid(ctx, m2, model->V0, v_pool.data());
-  const double V0p = model->V0 + eps;
+  const double V0p = model->V0 + eps5[4], V0m = model->V0 - eps5[4];
   v_grid(ctx, m2, V0p, v_pool.data() + (m2 + 1));
+  v_grid(ctx, m2, mode == HADI_MODE_JACOBIAN_CENTRAL ? V0m : model->V0, v_pool.data() + 2 * (m2 + 1));
   int idx_v0 = find_node(v_pool.data(), m2 + 1, model->V0);
   if (idx_v0 < 0) idx_v0 = 0;  // find_v0_index returns 0 when nothing matches (src/grid_pod.hpp:76-87)
   int idx_v1 = find_node(v_pool.data() + (m2 + 1), m2 + 1, V0p);
   if (idx_v1 < 0) idx_v1 = 0;
+  int idx_v2 = find_node(v_pool.data() + 2 * (m2 + 1), m2 + 1, V0m);
+  if (idx_v2 < 0) idx_v2 = 0;
+  int br_lo = 0, br_hi = 0;
+  double br_w = 0.0;
+  v0_bracket(v_pool.data(), m2, V0p, &br_lo, &br_hi, &br_w);
+  (void)br_w;  // applied by hadi_jacobian_assemble_ex
+  b->stride = (mode == HADI_MODE_JACOBIAN_INTERP) ? 3 : 1;
 
   for (int q = 0; q < n_items; ++q) {
     const int item = item_begin + q;
@@ -375,11 +460,16 @@ int hadi_batch_create(hadi_ctx* ctx, const hadi_model* model, const hadi_numeric
     it.eta = model->eta;
     it.sigma = model->sigma;
     it.rho = model->rho;
-    // bumps: src/jacobian_computation.cpp:299-304 (param + eps), :339 (grid for V0 + eps)
-    if (col == 1) it.kappa += eps;
-    if (col == 2) it.eta += eps;
-    if (col == 3) it.sigma += eps;
-    if (col == 4) it.rho += eps;
+    // bumps: src/jacobian_computation.cpp:299-304 (param + eps), :339 (grid for V0 + eps); columns 6..10
+    // are the downward bumps of the central-difference mode
+    if (col == 1) it.kappa += eps5[0];
+    if (col == 2) it.eta += eps5[1];
+    if (col == 3) it.sigma += eps5[2];
+    if (col == 4) it.rho += eps5[3];
+    if (col == 6) it.kappa -= eps5[0];
+    if (col == 7) it.eta -= eps5[1];
+    if (col == 8) it.sigma -= eps5[2];
+    if (col == 9) it.rho -= eps5[3];
     it.r_d = model->r_d;
     it.r_f = model->r_f;
     it.dt = pt.delta_t;
@@ -405,8 +495,9 @@ int hadi_batch_create(hadi_ctx* ctx, const hadi_model* model, const hadi_numeric
     sg = s_pool.data() + it.s_off;
     it.idx_s = find_node(sg, m1 + 1, model->S0);
     if (it.idx_s < 0) return fail(ctx, HADI_ERR_GRID, "S0 is not a node of the s-grid");
-    it.v_off = (col == 5) ? (m2 + 1) : 0;
-    it.idx_v = (col == 5) ? idx_v1 : idx_v0;
+    it.v_off = (col == 5) ? (m2 + 1) : (col == 10) ? 2 * (m2 + 1) : 0;
+    it.idx_v = (col == 5) ? idx_v1 : (col == 10) ? idx_v2 : idx_v0;
+    it.aux = br_lo | (br_hi << 16);
     auto ekey = std::make_pair(bits(pt.delta_t), pt.time_steps);
     auto eit = e_index.find(ekey);
     if (eit == e_index.end()) {
@@ -444,8 +535,8 @@ int hadi_batch_create(hadi_ctx* ctx, const hadi_model* model, const hadi_numeric
   };
   char* h_stage = (char*)take(staging, true);
   char* d_stage = (char*)take(staging, false);
-  b->h_values = (double*)take(sizeof(double) * (size_t)std::max(n_items, 1), true);
-  double* d_values = (double*)take(sizeof(double) * (size_t)std::max(n_items, 1), false);
+  b->h_values = (double*)take(sizeof(double) * (size_t)std::max(n_items, 1) * b->stride, true);
+  double* d_values = (double*)take(sizeof(double) * (size_t)std::max(n_items, 1) * b->stride, false);
   int* d_counter = (int*)take(256, false);
 
   b->plan = plan;
@@ -500,6 +591,7 @@ int hadi_batch_create(hadi_ctx* ctx, const hadi_model* model, const hadi_numeric
   L.scratch_stride = stride;
   L.counter = d_counter;
   L.out_values = d_values;
+  L.out_stride = b->stride;
   L.out_U = nullptr;
   L.out_lam = nullptr;
   L.scheme = num->scheme;
@@ -516,6 +608,7 @@ int hadi_batch_create(hadi_ctx* ctx, const hadi_model* model, const hadi_numeric
 }
 
 int hadi_batch_num_items(const hadi_batch* b) { return b ? b->n_items : 0; }
+int hadi_batch_values_per_item(const hadi_batch* b) { return b ? b->stride : 0; }
 double* hadi_batch_values_dev(hadi_batch* b) { return b ? b->L.out_values : nullptr; }
 
 int hadi_batch_launch(hadi_batch* b) {
@@ -539,13 +632,14 @@ int hadi_batch_fetch(hadi_batch* b, double* values) {
   if (!b || (!values && b->n_items > 0)) return HADI_ERR_ARG;
   hadi_ctx* ctx = b->ctx;
   cudaSetDevice(ctx->device);
-  cudaError_t e = cudaMemcpyAsync(b->h_values, b->L.out_values, sizeof(double) * (size_t)std::max(b->n_items, 1),
+  const size_t nv = (size_t)b->n_items * (size_t)b->stride;
+  cudaError_t e = cudaMemcpyAsync(b->h_values, b->L.out_values, sizeof(double) * std::max<size_t>(nv, 1),
                                   cudaMemcpyDeviceToHost, ctx->stream);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "D2H");
-  ctx->d2h_bytes += (long long)(sizeof(double) * (size_t)b->n_items);
+  ctx->d2h_bytes += (long long)(sizeof(double) * nv);
   e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "kernel execution");
-  if (b->n_items > 0) std::memcpy(values, b->h_values, sizeof(double) * (size_t)b->n_items);
+  if (nv > 0) std::memcpy(values, b->h_values, sizeof(double) * nv);
   return HADI_OK;
 }
 
@@ -598,11 +692,15 @@ void hadi_batch_destroy(hadi_batch* b) {
 }
 
 // ------------------------------------------------------------------------------------------------
+static const double kNoEps[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+static int values_per_item(int mode) { return mode == HADI_MODE_JACOBIAN_INTERP ? 3 : 1; }
+
+// values[(end - begin) * values_per_item(mode)]
 static int run_items(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
-                     const hadi_point* points, int mode, double eps, int begin, int end, double* values,
+                     const hadi_point* points, int mode, const double* eps5, int begin, int end, double* values,
                      double* U_out, double* lam_out, float* ms) {
   hadi_batch* b = nullptr;
-  int rc = hadi_batch_create(ctx, model, num, n, points, mode, eps, begin, end, &b);
+  int rc = hadi_batch_create_ex(ctx, model, num, n, points, mode, eps5, begin, end, &b);
   if (rc != HADI_OK) return rc;
   const size_t P = (size_t)(num->m1 + 1) * (size_t)(num->m2 + 1);
   int idU = -1, idL = -1;
@@ -636,7 +734,7 @@ int hadi_price_batch(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics
                      const hadi_point* points, double* prices, double* U_out, double* lambda_out) {
   if (!ctx || !prices) return HADI_ERR_ARG;
   std::vector<double> vals((size_t)std::max(n, 1));
-  const int rc = run_items(ctx, model, num, n, points, HADI_MODE_PRICE, 0.0, 0, -1, vals.data(), U_out, lambda_out, nullptr);
+  const int rc = run_items(ctx, model, num, n, points, HADI_MODE_PRICE, kNoEps, 0, -1, vals.data(), U_out, lambda_out, nullptr);
   if (rc != HADI_OK) return rc;
   // results land at CalibrationPoint::global_index, as in the reference's multi-maturity drivers
   for (int k = 0; k < n; ++k) {
@@ -649,11 +747,34 @@ int hadi_price_batch(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics
 
 int hadi_jacobian_batch(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
                         const hadi_point* points, double eps, double* J, double* base_prices) {
+  hadi_jacobian_options jo;
+  jo.mode = HADI_MODE_JACOBIAN;
+  for (int c = 0; c < 5; ++c) jo.eps[c] = eps;
+  return hadi_jacobian_batch_ex(ctx, model, num, n, points, &jo, J, base_prices);
+}
+
+static bool valid_jopt(const hadi_jacobian_options* jo) {
+  if (!jo) return false;
+  if (jo->mode != HADI_MODE_JACOBIAN && jo->mode != HADI_MODE_JACOBIAN_INTERP && jo->mode != HADI_MODE_JACOBIAN_CENTRAL)
+    return false;
+  for (int c = 0; c < 5; ++c)
+    if (!(jo->eps[c] > 0.0)) return false;
+  return true;
+}
+
+int hadi_jacobian_batch_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
+                           const hadi_point* points, const hadi_jacobian_options* jo, double* J,
+                           double* base_prices) {
   if (!ctx || !J || !base_prices) return HADI_ERR_ARG;
-  std::vector<double> vals((size_t)std::max(6 * n, 1)), Jt((size_t)std::max(5 * n, 1)), bt((size_t)std::max(n, 1));
-  int rc = run_items(ctx, model, num, n, points, HADI_MODE_JACOBIAN, eps, 0, -1, vals.data(), nullptr, nullptr, nullptr);
+  if (!model || !valid_numerics(num) || !valid_jopt(jo)) return fail(ctx, HADI_ERR_ARG, "bad argument");
+  const size_t per_option = (size_t)n_columns(jo->mode) * values_per_item(jo->mode);
+  std::vector<double> vals(std::max<size_t>(per_option * n, 1)), Jt((size_t)std::max(5 * n, 1)), bt((size_t)std::max(n, 1));
+  int rc = run_items(ctx, model, num, n, points, jo->mode, jo->eps, 0, -1, vals.data(), nullptr, nullptr, nullptr);
   if (rc != HADI_OK) return rc;
-  hadi_jacobian_assemble(n, vals.data(), eps, Jt.data(), bt.data());
+  int lo, hi;
+  double w = 0.0;
+  hadi_jacobian_v0_weight(num->m2, model->V0, jo->eps[4], &lo, &hi, &w);
+  hadi_jacobian_assemble_ex(n, jo->mode, vals.data(), jo->eps, w, Jt.data(), bt.data());
   for (int k = 0; k < n; ++k) {
     const int gi = points[k].global_index;
     if (gi < 0 || gi >= n) return fail(ctx, HADI_ERR_ARG, "global_index out of range");
@@ -727,25 +848,27 @@ int hadi_lm_update(int n, const double* J, const double* r, double lambda, doubl
   return hadi_solve5(A, g, delta);
 }
 
-// Solve the items of [0, n*nc) across the ranks of `comm` and return every item value on every rank.
+// Solve the items of [0, n*nc) across the ranks of `comm` and return every item value on every rank
+// (all[n * nc * values_per_item(mode)]).
 static int solve_all(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
-                     const hadi_point* points, int mode, double eps, const hadi_comm* comm, double* all,
+                     const hadi_point* points, int mode, const double* eps5, const hadi_comm* comm, double* all,
                      float* ms) {
-  const int nc = n_columns(mode);
+  const int nc = n_columns(mode), vpi = values_per_item(mode);
   const int total = n * nc;
   if (!comm || comm->world <= 1)
-    return run_items(ctx, model, num, n, points, mode, eps, 0, total, all, nullptr, nullptr, ms);
+    return run_items(ctx, model, num, n, points, mode, eps5, 0, total, all, nullptr, nullptr, ms);
   std::vector<int> costs((size_t)std::max(total, 1)), counts(comm->world), displs(comm->world);
   hadi_item_costs(num, n, points, mode, costs.data());
+  int my_begin = 0, my_end = 0;
   for (int r = 0; r < comm->world; ++r) {
     int b, e;
     hadi_partition(total, costs.data(), comm->world, r, &b, &e);
-    displs[r] = b;
-    counts[r] = e - b;
+    displs[r] = b * vpi;
+    counts[r] = (e - b) * vpi;
+    if (r == comm->rank) { my_begin = b; my_end = e; }
   }
   std::vector<double> mine((size_t)std::max(counts[comm->rank], 1));
-  int rc = run_items(ctx, model, num, n, points, mode, eps, displs[comm->rank], displs[comm->rank] + counts[comm->rank],
-                     mine.data(), nullptr, nullptr, ms);
+  int rc = run_items(ctx, model, num, n, points, mode, eps5, my_begin, my_end, mine.data(), nullptr, nullptr, ms);
   if (rc != HADI_OK) return rc;
   if (!comm->allgather) return fail(ctx, HADI_ERR_COMM, "no allgather hook");
   if (comm->allgather(comm->user, mine.data(), counts[comm->rank], all, counts.data(), displs.data(), comm->world) != 0)
@@ -758,22 +881,39 @@ static int solve_all(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics
 int hadi_calibrate(hadi_ctx* ctx, const hadi_model* initial, const hadi_numerics* num, int n,
                    const hadi_point* points, const double* market, const hadi_lm_options* opt,
                    const hadi_comm* comm, hadi_lm_result* res) {
+  if (!opt) return HADI_ERR_ARG;
+  hadi_jacobian_options jo;
+  jo.mode = HADI_MODE_JACOBIAN;
+  for (int c = 0; c < 5; ++c) jo.eps[c] = opt->eps;
+  return hadi_calibrate_ex(ctx, initial, num, n, points, market, opt, &jo, comm, res);
+}
+
+// The same loop with the Jacobian taken as `jo` says (opt->eps is ignored).
+// HADI_MODE_JACOBIAN reproduces the reference's trajectory; the other modes change the numbers.
+int hadi_calibrate_ex(hadi_ctx* ctx, const hadi_model* initial, const hadi_numerics* num, int n,
+                      const hadi_point* points, const double* market, const hadi_lm_options* opt,
+                      const hadi_jacobian_options* jo, const hadi_comm* comm, hadi_lm_result* res) {
   if (!ctx || !initial || !points || !market || !opt || !res || n <= 0) return HADI_ERR_ARG;
+  if (!valid_numerics(num) || !valid_jopt(jo)) return fail(ctx, HADI_ERR_ARG, "bad argument");
+  const int jcols = n_columns(jo->mode);
   for (int k = 0; k < n; ++k)
     if (points[k].global_index < 0 || points[k].global_index >= n) return fail(ctx, HADI_ERR_ARG, "global_index out of range");
   hadi_model cur = *initial;
   double lambda = opt->lambda0;
-  std::vector<double> vals((size_t)6 * n), J((size_t)5 * n), Jt((size_t)5 * n), base(n), bt(n), r(n), newp(n), nv(n);
+  std::vector<double> vals((size_t)jcols * values_per_item(jo->mode) * n), J((size_t)5 * n), Jt((size_t)5 * n), base(n), bt(n), r(n), newp(n), nv(n);
   bool converged = false;
   int iters = 0, solves = 0;
   double final_error = 100.0, delta_norm = 0.0, gpu_ms = 0.0;
   for (int iter = 0; iter < opt->max_iter && !converged; ++iter) {
     float ms = 0.f;
-    int rc = solve_all(ctx, &cur, num, n, points, HADI_MODE_JACOBIAN, opt->eps, comm, vals.data(), &ms);
+    int rc = solve_all(ctx, &cur, num, n, points, jo->mode, jo->eps, comm, vals.data(), &ms);
     if (rc != HADI_OK) return rc;
     gpu_ms += ms;
-    solves += 6 * n;
-    hadi_jacobian_assemble(n, vals.data(), opt->eps, Jt.data(), bt.data());
+    solves += jcols * n;
+    int blo, bhi;
+    double bw = 0.0;
+    hadi_jacobian_v0_weight(num->m2, cur.V0, jo->eps[4], &blo, &bhi, &bw);
+    hadi_jacobian_assemble_ex(n, jo->mode, vals.data(), jo->eps, bw, Jt.data(), bt.data());
     for (int k = 0; k < n; ++k) {
       const int gi = points[k].global_index;
       base[gi] = bt[k];
@@ -800,7 +940,7 @@ int hadi_calibrate(hadi_ctx* ctx, const hadi_model* initial, const hadi_numerics
       iters = iter + 1;
       break;
     }
-    rc = solve_all(ctx, &nw, num, n, points, HADI_MODE_PRICE, 0.0, comm, nv.data(), &ms);
+    rc = solve_all(ctx, &nw, num, n, points, HADI_MODE_PRICE, kNoEps, comm, nv.data(), &ms);
     if (rc != HADI_OK) return rc;
     gpu_ms += ms;
     solves += n;

@@ -84,6 +84,20 @@ __device__ __forceinline__ void hadi_dbg_check_lam(const HadiLaunch& L, const Ha
 }
 #endif
 
+// Item result: the price at (S0, V0) (src/jacobian_computation.cpp:275-287,330).  Batches that take the V0
+// column of the Jacobian by interpolation (src/device_solver.cpp:1725-1829) publish three values per item:
+// the price and U at the two v-rows bracketing V0 + eps on the S0 column (HadiItem::aux packs them).
+__device__ __forceinline__ void hadi_publish(const HadiLaunch& L, const HadiItem& it, const HadiView& w) {
+  if (L.out_stride <= 1) {
+    L.out_values[it.out] = w.U[it.idx_v * w.ld + it.idx_s];
+  } else {
+    double* o = L.out_values + (size_t)it.out * L.out_stride;
+    o[0] = w.U[it.idx_v * w.ld + it.idx_s];
+    o[1] = w.U[(it.aux & 0xffff) * w.ld + it.idx_s];
+    o[2] = w.U[((it.aux >> 16) & 0xffff) * w.ld + it.idx_s];
+  }
+}
+
 // One item, payoff to price.  Returns (CTA-uniform) whether any guarded division left its fast-path
 // range; EXACT = true compiles every division as IEEE '/'.
 // FEED == 4: co-operative S1 / pipelined S2 of hadi_phases_fast.cuh (grid-specialised variants only)
@@ -105,6 +119,9 @@ __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiI
   unsigned bad = 0;
 
   hadi_phase_tables(it, w, sg, vg, tid, NT);
+#ifdef HADI_PFW
+  if (tid == 0) w.divk[w.n1 - 1] = 0;   // chunk counter of the L1 warm-up warp (spare word behind the dividend indices)
+#endif
   if constexpr (hadi_is_coop<Feed>::value && M1 > 0) {
     // staged / consumed block counters of the co-operative S1 (hadi_phases_fast.cuh)
     if (tid < 2 * hadi_co_warps(M2))
@@ -405,7 +422,7 @@ __global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch
 #endif
     }
 
-    if (tid == 0) L.out_values[it.out] = w.U[it.idx_v * w.ld + it.idx_s];
+    if (tid == 0) hadi_publish(L, it, w);
 #ifdef HADI_DEBUG_TRACE
     if (false) {
 #else
@@ -563,7 +580,7 @@ __global__ void __cluster_dims__(HADI_CLUSTER, 1, 1) __launch_bounds__(NT, 1) ha
       if (gtid == 0 && L.prof != nullptr) atomicAdd((unsigned long long*)&L.prof[(size_t)gridDim.x * 8], 1ULL);
       hadi_cluster_solve<NT, true>(L, it, w, cs, tid, gtid, gnt, mail);
     }
-    if (gtid == 0) L.out_values[it.out] = w.U[it.idx_v * w.ld + it.idx_s];
+    if (gtid == 0) hadi_publish(L, it, w);
     if (L.out_U != nullptr || L.out_lam != nullptr) {
       const HadiMap mp = hadi_map(m1, m2, gtid, gnt);
       if (mp.active) {

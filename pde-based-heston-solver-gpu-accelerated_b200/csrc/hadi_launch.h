@@ -21,7 +21,8 @@ struct HadiLaunch {
   double* scratch;           // device, per-CTA-slot scratch (A1 factors, lambda)
   size_t scratch_stride;     // doubles per CTA slot
   int* counter;              // device work counter (zeroed before launch)
-  double* out_values;        // [n_items] price at (S0, V0) per item (slot item.out)
+  double* out_values;        // [n_items][out_stride] price at (S0, V0) per item (slot item.out)
+  int out_stride;            // values per item: 1, or 3 = {price, U(S0, v_lower), U(S0, v_upper)} (interpolated-V0 Jacobian)
   double* out_U;             // optional [n_items][P] natural layout
   double* out_lam;           // optional [n_items][P]
   long long* prof;           // optional [gridDim.x][8] phase cycle counters (HADI_PHASE_TIMING builds only)

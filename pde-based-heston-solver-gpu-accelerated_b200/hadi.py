@@ -20,7 +20,9 @@ OK, ERR_ARG, ERR_GRID, ERR_CUDA, ERR_SMEM, ERR_COMM, ERR_NOMEM = 0, -1, -2, -3, 
 EUROPEAN, AMERICAN = 0, 1
 CALL, PUT = 0, 1
 DOUGLAS, CRAIG_SNEYD = 0, 1
-MODE_PRICE, MODE_JACOBIAN = 0, 1
+MODE_PRICE, MODE_JACOBIAN, MODE_JACOBIAN_INTERP, MODE_JACOBIAN_CENTRAL = 0, 1, 2, 3
+ITEMS_PER_OPTION = {0: 1, 1: 6, 2: 5, 3: 11}
+VALUES_PER_ITEM = {0: 1, 1: 1, 2: 3, 3: 1}
 
 # every symbol include/hadi.h declares (checked by tests/test_abi.py)
 EXPORTS = [
@@ -31,6 +33,8 @@ EXPORTS = [
     "hadi_lm_update", "hadi_calibrate", "hadi_grid", "hadi_bs_call", "hadi_transfer_bytes", "hadi_measure_fp64",
     "hadi_batch_phase_cycles", "hadi_bs_vega", "hadi_bs_implied_vol", "hadi_bs_implied_vol_bisect",
     "hadi_dividend_adjusted_spot", "hadi_market_prices", "hadi_implied_vols", "hadi_write_calibration_csv",
+    "hadi_batch_create_ex", "hadi_batch_values_per_item", "hadi_jacobian_assemble_ex", "hadi_jacobian_v0_weight",
+    "hadi_jacobian_batch_ex", "hadi_calibrate_ex",
 ]
 
 
@@ -58,6 +62,19 @@ class LmResult(C.Structure):
     _fields_ = [("params", C.c_double * 5), ("final_error", C.c_double), ("lambda_", C.c_double),
                 ("delta_norm", C.c_double), ("iterations", C.c_int), ("converged", C.c_int),
                 ("pde_solves", C.c_int), ("gpu_ms", C.c_double)]
+
+
+class JacobianOptions(C.Structure):
+    _fields_ = [("mode", C.c_int), ("eps", C.c_double * 5)]
+
+
+def make_jacobian_options(mode=MODE_JACOBIAN, eps=1e-6):
+    jo = JacobianOptions()
+    jo.mode = mode
+    e = np.broadcast_to(np.asarray(eps, dtype=np.float64), (5,))
+    for k in range(5):
+        jo.eps[k] = float(e[k])
+    return jo
 
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, _dp, C.c_int, _dp, _ip, _ip, C.c_int)
@@ -120,6 +137,16 @@ def lib():
         L.hadi_transfer_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
         L.hadi_measure_fp64.argtypes = [C.c_int] + [C.POINTER(C.c_double)] * 3
         L.hadi_batch_phase_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_longlong)]
+        L.hadi_batch_create_ex.argtypes = [C.c_void_p, C.POINTER(Model), C.POINTER(Numerics), C.c_int,
+                                           C.POINTER(Point), C.c_int, _dp, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.hadi_batch_values_per_item.argtypes = [C.c_void_p]
+        L.hadi_jacobian_assemble_ex.argtypes = [C.c_int, C.c_int, _dp, _dp, C.c_double, _dp, _dp]
+        L.hadi_jacobian_v0_weight.argtypes = [C.c_int, C.c_double, C.c_double, _ip, _ip, _dp]
+        L.hadi_jacobian_batch_ex.argtypes = [C.c_void_p, C.POINTER(Model), C.POINTER(Numerics), C.c_int,
+                                             C.POINTER(Point), C.POINTER(JacobianOptions), _dp, _dp]
+        L.hadi_calibrate_ex.argtypes = [C.c_void_p, C.POINTER(Model), C.POINTER(Numerics), C.c_int,
+                                        C.POINTER(Point), _dp, C.POINTER(LmOptions), C.POINTER(JacobianOptions),
+                                        C.POINTER(Comm), C.POINTER(LmResult)]
         L.hadi_bs_vega.argtypes = [C.c_double] * 5
         L.hadi_bs_vega.restype = C.c_double
         L.hadi_bs_implied_vol.argtypes = [C.c_double] * 7
@@ -290,7 +317,7 @@ def partition(costs, world, rank):
 
 
 def item_costs(num, pts, n, mode):
-    nc = 6 if mode == MODE_JACOBIAN else 1
+    nc = ITEMS_PER_OPTION[mode]
     costs = np.zeros(max(n * nc, 1), dtype=np.int32)
     rc = lib().hadi_item_costs(C.byref(num.num), n, pts, mode, costs.ctypes.data_as(_ip))
     if rc != OK:
@@ -303,6 +330,25 @@ def jacobian_assemble(values, eps):
     n = values.size // 6
     J, base = np.zeros((n, 5)), np.zeros(n)
     rc = lib().hadi_jacobian_assemble(n, _d(values), eps, _d(J), _d(base))
+    if rc != OK:
+        raise HadiError(rc)
+    return J, base
+
+
+def jacobian_v0_weight(m2, V0, eps_v0):
+    lo, hi, w = C.c_int(0), C.c_int(0), C.c_double(0.0)
+    rc = lib().hadi_jacobian_v0_weight(m2, V0, eps_v0, C.byref(lo), C.byref(hi), C.byref(w))
+    if rc != OK:
+        raise HadiError(rc)
+    return lo.value, hi.value, w.value
+
+
+def jacobian_assemble_ex(values, mode, eps5, v0_weight=0.0):
+    values = np.ascontiguousarray(values, dtype=np.float64)
+    eps5 = np.ascontiguousarray(np.broadcast_to(np.asarray(eps5, dtype=np.float64), (5,)))
+    n = values.size // (ITEMS_PER_OPTION[mode] * VALUES_PER_ITEM[mode])
+    J, base = np.zeros((n, 5)), np.zeros(n)
+    rc = lib().hadi_jacobian_assemble_ex(n, mode, _d(values), _d(eps5), v0_weight, _d(J), _d(base))
     if rc != OK:
         raise HadiError(rc)
     return J, base
@@ -362,15 +408,30 @@ class Context:
                                               _d(base)))
         return J[:n], base[:n]
 
+    def jacobian_batch_ex(self, model, num, pts, n, mode, eps=1e-6):
+        """Jacobian taken as `mode` says (forward / interpolated V0 column / central), eps scalar or [5]."""
+        jo = make_jacobian_options(mode, eps)
+        J, base = np.zeros((max(n, 1), 5)), np.zeros(max(n, 1))
+        self._check(lib().hadi_jacobian_batch_ex(self._h, C.byref(model), C.byref(num.num), n, pts, C.byref(jo),
+                                                 _d(J), _d(base)))
+        return J[:n], base[:n]
+
     def batch(self, model, num, pts, n, mode=MODE_PRICE, eps=1e-6, begin=0, end=-1):
         return Batch(self, model, num, pts, n, mode, eps, begin, end)
 
-    def calibrate(self, model, num, pts, n, market, max_iter, tol, delta_tol, lambda0=0.01, eps=1e-6, comm=None):
+    def calibrate(self, model, num, pts, n, market, max_iter, tol, delta_tol, lambda0=0.01, eps=1e-6, comm=None,
+                  jac_mode=None):
         market = np.ascontiguousarray(market, dtype=np.float64)
-        opt = LmOptions(max_iter, tol, delta_tol, lambda0, eps)
+        opt = LmOptions(max_iter, tol, delta_tol, lambda0, float(np.atleast_1d(eps)[0]))
         res = LmResult()
-        self._check(lib().hadi_calibrate(self._h, C.byref(model), C.byref(num.num), n, pts, _d(market),
-                                         C.byref(opt), None if comm is None else C.byref(comm), C.byref(res)))
+        if jac_mode is None:
+            self._check(lib().hadi_calibrate(self._h, C.byref(model), C.byref(num.num), n, pts, _d(market),
+                                             C.byref(opt), None if comm is None else C.byref(comm), C.byref(res)))
+        else:
+            jo = make_jacobian_options(jac_mode, eps)
+            self._check(lib().hadi_calibrate_ex(self._h, C.byref(model), C.byref(num.num), n, pts, _d(market),
+                                                C.byref(opt), C.byref(jo),
+                                                None if comm is None else C.byref(comm), C.byref(res)))
         return dict(params=list(res.params), final_error=res.final_error, lam=res.lambda_,
                     delta_norm=res.delta_norm, iterations=res.iterations, converged=res.converged,
                     pde_solves=res.pde_solves, gpu_ms=res.gpu_ms)
@@ -383,17 +444,20 @@ class Batch:
         self.ctx = ctx
         self._keep = (model, num, pts)
         self._h = C.c_void_p()
-        ctx._check(lib().hadi_batch_create(ctx._h, C.byref(model), C.byref(num.num), n, pts, mode, eps, begin, end,
-                                           C.byref(self._h)))
+        eps5 = np.ascontiguousarray(np.broadcast_to(np.asarray(eps, dtype=np.float64), (5,)))
+        ctx._check(lib().hadi_batch_create_ex(ctx._h, C.byref(model), C.byref(num.num), n, pts, mode, _d(eps5),
+                                              begin, end, C.byref(self._h)))
         self.n_items = lib().hadi_batch_num_items(self._h)
+        self.values_per_item = lib().hadi_batch_values_per_item(self._h)
 
     def launch(self):
         self.ctx._check(lib().hadi_batch_launch(self._h))
 
     def fetch(self):
-        vals = np.zeros(max(self.n_items, 1))
+        nv = self.n_items * self.values_per_item
+        vals = np.zeros(max(nv, 1))
         self.ctx._check(lib().hadi_batch_fetch(self._h, _d(vals)))
-        return vals[:self.n_items]
+        return vals[:nv]
 
     def elapsed_ms(self):
         ms = C.c_float(0.0)

@@ -41,7 +41,8 @@ def solve_items_sharded(hadi, num, pts, n, mode, local_solve, rank, world, devic
     mine = local_solve(b, e) if e > b else np.zeros(0)
     if world == 1:
         return np.asarray(mine, dtype=np.float64)
-    return allgather_values(mine, [x[1] - x[0] for x in sl], dist=dist, device=device)
+    vpi = hadi.VALUES_PER_ITEM[mode]   # an item of the interpolated-V0 Jacobian publishes three values
+    return allgather_values(mine, [(x[1] - x[0]) * vpi for x in sl], dist=dist, device=device)
 
 
 def make_comm(hadi, rank, world, device=None, dist=None):

@@ -376,3 +376,103 @@ def test_config4_full_size_golden(hadi, ctx):
     assert np.all(g["prices"] == 8.8920027296371611)
     g = solve_gpu(hadi, ctx, [100.0], 200, 1.0, 400, 200)
     assert g["prices"][0] == 8.8925021574843157
+
+
+def test_interpolated_v0_jacobian(hadi, ctx, oracle):
+    """SURVEY 8(f) rank 1, opt-in: the V0 column from the base solve, interpolated linearly in v between the
+    rows bracketing V0 + eps exactly as the reference's prototype does (src/device_solver.cpp:1735-1818);
+    the other four columns stay the reference's forward differences.  Checked against the same formula
+    applied to the oracle's full base-solve grid, bit for bit."""
+    m1, m2, N, eps = 50, 25, 20, 1e-6
+    strikes = [92.0, 100.0, 107.5]
+    mdl = hadi.make_model(**BASE)
+    num = hadi.make_numerics(m1, m2, 0.8)
+    pts, n = hadi.make_points(strikes, 1.0, N)
+    before = ctx.kernel_launches
+    J, base = ctx.jacobian_batch_ex(mdl, num, pts, n, hadi.MODE_JACOBIAN_INTERP, eps)
+    assert ctx.kernel_launches == before + 1
+    Jf, basef = ctx.jacobian_batch(mdl, num, pts, n, eps)
+    assert np.array_equal(base, basef) and np.array_equal(J[:, :4], Jf[:, :4])
+    lo, hi, w = hadi.jacobian_v0_weight(m2, BASE["V0"], eps)
+    s, v = hadi.grid(m1, m2, 100.0, BASE["S0"], BASE["V0"])
+    assert v[lo] <= BASE["V0"] + eps <= v[hi] and hi == lo + 1
+    assert w == (BASE["V0"] + eps - v[lo]) / (v[hi] - v[lo])
+    for k, K in enumerate(strikes):
+        o = oracle.solve(K, N, 1.0 / N, m1=m1, m2=m2, theta=0.8, style=0, divs=None, payoff_put=0, **BASE)
+        sg, _ = hadi.grid(m1, m2, K, BASE["S0"], BASE["V0"])
+        i_s = int(np.argmax(np.abs(sg - BASE["S0"]) < 1e-10))
+        U = np.asarray(o["U"]).reshape(m2 + 1, m1 + 1)
+        pert = U[lo, i_s] + w * (U[hi, i_s] - U[lo, i_s])
+        assert J[k, 4] == (pert - o["price"]) / eps
+        # and it approximates the forward-difference column it replaces (the interpolation error of a
+        # linear bracket in v, not rounding: a few per cent at this resolution)
+        assert abs(J[k, 4] - Jf[k, 4]) <= 0.05 * abs(Jf[k, 4])
+    # sliced (multi-GPU style) batches publish three values per item and reassemble to the same Jacobian
+    full = ctx.batch(mdl, num, pts, n, hadi.MODE_JACOBIAN_INTERP, eps)
+    assert full.n_items == 5 * n and full.values_per_item == 3
+    full.launch()
+    vals = full.fetch().copy()
+    costs = hadi.item_costs(num, pts, n, hadi.MODE_JACOBIAN_INTERP)
+    parts = []
+    for r in range(3):
+        b, e = hadi.partition(costs, 3, r)
+        bt = ctx.batch(mdl, num, pts, n, hadi.MODE_JACOBIAN_INTERP, eps, b, e)
+        bt.launch()
+        parts.append(bt.fetch().copy())
+        bt.destroy()
+    assert np.array_equal(np.concatenate(parts), vals)
+    J2, base2 = hadi.jacobian_assemble_ex(vals, hadi.MODE_JACOBIAN_INTERP, eps, w)
+    assert np.array_equal(J2, J) and np.array_equal(base2, base)
+
+
+def test_central_difference_jacobian_and_per_parameter_eps(hadi, ctx, oracle):
+    """Opt-in central differences with one bump per parameter: every one of the 11 solves per option is the
+    oracle's price at the bumped parameters, bit for bit."""
+    m1, m2, N = 50, 25, 20
+    eps5 = [1e-5, 2e-6, 1e-5, 3e-6, 1e-6]
+    strikes = [95.0, 104.0]
+    mdl = hadi.make_model(**BASE)
+    num = hadi.make_numerics(m1, m2, 0.8, hadi.AMERICAN, hadi.CALL, hadi.DOUGLAS, DIVS)
+    pts, n = hadi.make_points(strikes, 1.0, N)
+    J, base = ctx.jacobian_batch_ex(mdl, num, pts, n, hadi.MODE_JACOBIAN_CENTRAL, eps5)
+    names = ["kappa", "eta", "sigma", "rho", "V0"]
+    for k, K in enumerate(strikes):
+        def price(**bump):
+            p = dict(BASE)
+            for key, d in bump.items():
+                p[key] = p[key] + d
+            return oracle.solve(K, N, 1.0 / N, m1=m1, m2=m2, theta=0.8, style=1, divs=DIVS, payoff_put=0,
+                                want_U=False, want_lambda=False, **p)["price"]
+        assert base[k] == price()
+        for c, name in enumerate(names):
+            up, dn = price(**{name: eps5[c]}), price(**{name: -eps5[c]})
+            assert J[k, c] == (up - dn) / (2.0 * eps5[c])
+    # forward differences with per-parameter bumps through the same entry point
+    Jf, basef = ctx.jacobian_batch_ex(mdl, num, pts, n, hadi.MODE_JACOBIAN, eps5)
+    assert np.array_equal(basef, base)
+    # central and forward differences agree to O(eps) relative to the column scale
+    assert np.all(np.abs(J - Jf) <= 1e-3 * (1.0 + np.abs(Jf)))
+    with pytest.raises(hadi.HadiError):
+        ctx.jacobian_batch_ex(mdl, num, pts, n, hadi.MODE_JACOBIAN_CENTRAL, [1e-6, 1e-6, 1e-6, 1e-6, 1.0])  # V0 - eps <= 0
+
+
+def test_lm_with_interpolated_v0_column(hadi, ctx):
+    """hadi_calibrate_ex with the 5-solve Jacobian: one sixth fewer PDE solves per iteration; the default mode
+    through the same entry point reproduces the reference trajectory."""
+    mats = [1.0, 1.5, 2.0]
+    strikes = [95.0 + 2.0 * i for i in range(6)]
+    K = [k for _ in mats for k in strikes]
+    T = [t for t in mats for _ in strikes]
+    N = [max(20, int(20 * t)) for t in T]
+    pts, n = hadi.make_points(K, T, N)
+    market = hadi.market_prices(100.0, 0.025, 0.2, pts, n)
+    mdl, num = hadi.make_model(**BASE), hadi.make_numerics(50, 25, 0.8)
+    tol, dtol = 0.1 * math.sqrt(n), 0.1 * (1.0 + math.log(n))
+    ref = ctx.calibrate(mdl, num, pts, n, market, 15, tol, dtol)
+    same = ctx.calibrate(mdl, num, pts, n, market, 15, tol, dtol, jac_mode=hadi.MODE_JACOBIAN)
+    assert same["params"] == ref["params"] and same["pde_solves"] == ref["pde_solves"]
+    itp = ctx.calibrate(mdl, num, pts, n, market, 15, tol, dtol, jac_mode=hadi.MODE_JACOBIAN_INTERP)
+    assert itp["converged"] == 1
+    jac_calls = itp["iterations"]
+    assert itp["pde_solves"] == jac_calls * 5 * n + (jac_calls - 1) * n
+    assert itp["final_error"] <= 2.0 * ref["final_error"] + tol

@@ -151,3 +151,43 @@ def test_calibration_report_writer(hadi, tmp_path):
     assert lines[0].startswith("# 4 options, Time=0.25 s, FinalError=1.25, iterationCount=3, TotalPdeSolves=160, init_kappa=1.5")
     assert lines[1] == "Strike,MarketPrice,FittedPrice,IVDifference" and len(lines) == 2 + n1
     assert lines[2].split(",")[0] == "95"
+
+
+def test_jacobian_assembly_of_every_mode(hadi):
+    """Layouts of include/hadi.h: forward (6 values per option), interpolated V0 (5 items x 3 values),
+    central (11 values); and the v-bracket of the interpolation (src/device_solver.cpp:1735-1754)."""
+    rng = np.random.default_rng(5)
+    n, eps5 = 4, np.array([1e-6, 2e-6, 3e-6, 4e-6, 5e-6])
+    v = rng.normal(size=6 * n)
+    J, base = hadi.jacobian_assemble_ex(v, hadi.MODE_JACOBIAN, eps5)
+    for k in range(n):
+        assert base[k] == v[6 * k]
+        for c in range(5):
+            assert J[k, c] == (v[6 * k + 1 + c] - v[6 * k]) / eps5[c]
+    J1, base1 = hadi.jacobian_assemble(v, 1e-6)
+    J2, base2 = hadi.jacobian_assemble_ex(v, hadi.MODE_JACOBIAN, 1e-6)
+    assert np.array_equal(J1, J2) and np.array_equal(base1, base2)
+    v = rng.normal(size=15 * n)
+    w = 0.37
+    J, base = hadi.jacobian_assemble_ex(v, hadi.MODE_JACOBIAN_INTERP, eps5, w)
+    for k in range(n):
+        o = v[15 * k:15 * k + 15]
+        assert base[k] == o[0]
+        for c in range(4):
+            assert J[k, c] == (o[3 * (1 + c)] - o[0]) / eps5[c]
+        assert J[k, 4] == ((o[1] + w * (o[2] - o[1])) - o[0]) / eps5[4]
+    v = rng.normal(size=11 * n)
+    J, base = hadi.jacobian_assemble_ex(v, hadi.MODE_JACOBIAN_CENTRAL, eps5)
+    for k in range(n):
+        assert base[k] == v[11 * k]
+        for c in range(5):
+            assert J[k, c] == (v[11 * k + 1 + c] - v[11 * k + 6 + c]) / (2.0 * eps5[c])
+    _, vg = hadi.grid(50, 25, 100.0, 100.0, 0.04)
+    lo, hi, wt = hadi.jacobian_v0_weight(25, 0.04, 1e-6)
+    assert vg[lo] == 0.04 and hi == lo + 1 and wt == (0.04 + 1e-6 - vg[lo]) / (vg[hi] - vg[lo])
+    # a bump beyond the last v-node finds no bracket: the reference leaves index 0 / weight 0
+    assert hadi.jacobian_v0_weight(25, 0.04, 10.0) == (0, 0, 0.0)
+    num = hadi.make_numerics(100, 50, 0.8)
+    pts, n3 = hadi.make_points([90.0, 100.0], [1.0, 2.0], [20, 40])
+    assert hadi.item_costs(num, pts, n3, hadi.MODE_JACOBIAN_INTERP).size == 10
+    assert hadi.item_costs(num, pts, n3, hadi.MODE_JACOBIAN_CENTRAL).size == 22
