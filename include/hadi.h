@@ -190,6 +190,15 @@ int hadi_partition(int n_items, const int* costs, int world, int rank, int* begi
 /* cost (N*P) of each item of a would-be batch, for hadi_partition; costs[n * items per option] */
 int hadi_item_costs(const hadi_numerics* num, int n, const hadi_point* points, int mode, int* costs);
 
+/* Inspection aid: the split schedule a batch of n solves of time_steps[k] steps gets on `slots` persistent CTAs.
+ * When a batch holds more solves than CTAs, the one solve that straddles the end of a CTA's share is cut in two
+ * (its first steps open the next CTA's list, its state is handed over through L2), so that all CTAs finish
+ * together instead of after a whole number of solves.  seg5[5*q] = {item, first step, last step, hand-off in,
+ * hand-off out}, slot_off[slots+1]; `setup` = cost of a segment's set-up in steps (the library uses 1.5).
+ * Returns the number of segments, 0 when nothing is cut (n <= slots). */
+int hadi_plan_schedule(int n, const int* time_steps, int slots, double setup, int max_segments, int* seg5,
+                       int* slot_off, double* heaviest_steps);
+
 /* ---- Levenberg-Marquardt ---------------------------------------------------------------------- */
 int hadi_solve5(const double* A, const double* b, double* x);
 int hadi_lm_update(int n, const double* J, const double* residual, double lambda, double* delta);

@@ -54,6 +54,7 @@ struct hadi_batch {
   hadi_ctx* ctx = nullptr;
   int n_items = 0;
   int stride = 1;  // values per item (3 in HADI_MODE_JACOBIAN_INTERP)
+  int n_hand = 0;  // hand-off slots of the split schedule (0: CTAs pull whole items from the counter)
   int m1 = 0, m2 = 0;
   HadiLaunch L{};
   HadiPlan plan{};
@@ -188,6 +189,80 @@ bool valid_numerics(const hadi_numerics* num) {
   return true;
 }
 
+// Split schedule (McNaughton's wrap-around rule for preemptive scheduling on identical machines): the batch is
+// n solves of N_k time steps on `slots` persistent CTAs.  Whole solves per CTA quantise the makespan to a whole
+// number of solves per CTA (500 solves on 296 CTAs take as long as 592); cutting the one solve that straddles
+// the end of a CTA's share in two makes every CTA finish after T = total / slots steps.  The LAST steps of a
+// cut solve close the list of CTA b, its FIRST steps open the list of CTA b + 1, so the state (U, lambda)
+// is ready long before it is needed whenever T >= N + 2 set-ups.  Costs are in time steps; `setup` is what a
+// segment pays before its first step (tables, factorisation; measured ~1.3 steps at 101x51).
+struct SplitSchedule {
+  std::vector<HadiSegment> segs;
+  std::vector<int> off;   // [slots + 1]
+  int n_hand = 0;
+};
+// One pass of the rule for a given target T; returns the load (steps) of the heaviest CTA.
+double fill_split_schedule(const std::vector<HadiItem>& items, int slots, double setup, double T, SplitSchedule* out) {
+  const int n = (int)items.size();
+  const int min_seg = 3;   // a cut that leaves fewer steps than this on either side is not worth a set-up
+  out->segs.clear();
+  out->off.assign(1, 0);
+  out->n_hand = 0;
+  int slot = 0;
+  double used = 0.0, heaviest = 0.0;
+  auto close_slot = [&]() {
+    heaviest = std::max(heaviest, used);
+    out->off.push_back((int)out->segs.size());
+    ++slot;
+    used = 0.0;
+  };
+  for (int k = 0; k < n; ++k) {
+    const int N = items[k].N;
+    const double room = T - used - setup;
+    if (slot >= slots - 1 || room >= N) {
+      out->segs.push_back(HadiSegment{k, 1, N, -1, -1, 0, 0, 0});
+      used += setup + N;
+      continue;
+    }
+    int tail = (int)room;   // steps of this solve that still fit
+    if (tail > N - min_seg) tail = N - min_seg;   // nearly all of it fits: leave min_seg steps for the next CTA
+    if (tail < min_seg) {
+      close_slot();
+      out->segs.push_back(HadiSegment{k, 1, N, -1, -1, 0, 0, 0});
+      used += setup + N;
+      continue;
+    }
+    const int h = out->n_hand++;
+    out->segs.push_back(HadiSegment{k, N - tail + 1, N, h, -1, 0, 0, 0});   // closes this CTA's list
+    used += setup + tail;
+    close_slot();
+    out->segs.push_back(HadiSegment{k, 1, N - tail, -1, h, 0, 0, 0});       // opens the next CTA's list
+    used += setup + (N - tail);
+  }
+  heaviest = std::max(heaviest, used);
+  while ((int)out->off.size() < slots + 1) out->off.push_back((int)out->segs.size());
+  return heaviest;
+}
+bool build_split_schedule(const std::vector<HadiItem>& items, int slots, double setup, SplitSchedule* out) {
+  const int n = (int)items.size();
+  if (slots < 2 || n <= slots) return false;
+  double total = 0.0, longest = 0.0;
+  for (const HadiItem& it : items) {
+    total += it.N + setup;
+    longest = std::max(longest, it.N + setup);
+  }
+  // every CTA but the last may end with a cut: one more set-up each.  Cuts fall on whole steps and slivers
+  // shorter than min_seg are left unused, so the last CTA collects what the others could not place: raise T
+  // until it is no heavier than the rest.
+  double T = std::max(longest, (total + (slots - 1) * setup) / slots);
+  for (int iter = 0; iter < 64; ++iter) {
+    const double heaviest = fill_split_schedule(items, slots, setup, T, out);
+    if (heaviest <= T + 1e-9) break;
+    T += std::max(0.125, (heaviest - T) / slots);
+  }
+  return out->n_hand > 0;
+}
+
 // work items per option: base + one per bumped parameter
 int n_columns(int mode) {
   switch (mode) {
@@ -315,6 +390,37 @@ int hadi_partition(int n_items, const int* costs, int world, int rank, int* begi
   *begin = boundary(rank);
   *end = boundary(rank + 1);
   return HADI_OK;
+}
+
+// Inspection / test aid: the split schedule hadi_batch_create builds for n solves of time_steps[k] steps
+// (in the order given) on `slots` persistent CTAs.
+int hadi_plan_schedule(int n, const int* time_steps, int slots, double setup, int max_segments, int* seg5,
+                       int* slot_off, double* heaviest_steps) {
+  if (n < 0 || (n > 0 && !time_steps) || slots < 1 || !seg5 || !slot_off) return HADI_ERR_ARG;
+  std::vector<HadiItem> items((size_t)n);
+  for (int k = 0; k < n; ++k) {
+    if (time_steps[k] < 1) return HADI_ERR_ARG;
+    std::memset(&items[k], 0, sizeof(HadiItem));
+    items[k].N = time_steps[k];
+  }
+  SplitSchedule sc;
+  if (!build_split_schedule(items, slots, setup, &sc)) return 0;
+  if ((int)sc.segs.size() > max_segments) return HADI_ERR_ARG;
+  for (size_t q = 0; q < sc.segs.size(); ++q) {
+    seg5[5 * q + 0] = sc.segs[q].item; seg5[5 * q + 1] = sc.segs[q].n0; seg5[5 * q + 2] = sc.segs[q].n1;
+    seg5[5 * q + 3] = sc.segs[q].hin;  seg5[5 * q + 4] = sc.segs[q].hout;
+  }
+  for (int b = 0; b <= slots; ++b) slot_off[b] = sc.off[b];
+  if (heaviest_steps) {
+    double hv = 0.0;
+    for (int b = 0; b < slots; ++b) {
+      double u = 0.0;
+      for (int q = sc.off[b]; q < sc.off[b + 1]; ++q) u += setup + (sc.segs[q].n1 - sc.segs[q].n0 + 1);
+      hv = std::max(hv, u);
+    }
+    *heaviest_steps = hv;
+  }
+  return (int)sc.segs.size();
 }
 
 int hadi_jacobian_assemble(int n, const double* v, double eps, double* J, double* base) {
@@ -515,6 +621,18 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
   // longest items first (the persistent CTAs pull items in order)
   std::stable_sort(items.begin(), items.end(), [](const HadiItem& a, const HadiItem& c) { return a.cost > c.cost; });
 
+  // split schedule for the shared-memory resident kernels (the ring-fed and global-state kernels keep whole items)
+  SplitSchedule sched;
+  bool use_split = false;
+  {
+    const int slots = plan.ctas_per_sm * plan.sm_count;
+    const char* ns = getenv("HADI_NO_SPLIT");
+    const char* su = getenv("HADI_SPLIT_SETUP");
+    const double setup = su ? atof(su) : 1.5;
+    if (!(ns && atoi(ns) != 0) && !plan.global_state && plan.cluster <= 1 && plan.variant <= 3 && !getenv("HADI_MAX_CTAS"))
+      use_split = build_split_schedule(items, slots, setup, &sched);
+  }
+
   // ---- device buffers ------------------------------------------------------------------------
   const int nd = num->num_dividends;
   const size_t bytes_items = sizeof(HadiItem) * (size_t)std::max(n_items, 1);
@@ -522,7 +640,8 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
   const size_t bytes_v = sizeof(double) * v_pool.size();
   const size_t bytes_e = sizeof(double) * std::max<size_t>(e_pool.size(), 1);
   const size_t bytes_d = sizeof(double) * (size_t)std::max(3 * nd, 1);
-  const size_t staging = bytes_items + bytes_s + bytes_v + bytes_e + bytes_d + 5 * 256;
+  const size_t bytes_sg = use_split ? sizeof(HadiSegment) * sched.segs.size() + sizeof(int) * sched.off.size() : 0;
+  const size_t staging = bytes_items + bytes_s + bytes_v + bytes_e + bytes_d + bytes_sg + 8 * 256;
 
   auto take = [&](size_t bytes, bool pinned) -> void* {
     const int id = pool_get(ctx, bytes, pinned);
@@ -569,6 +688,11 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
     dv[2 * nd + k] = num->dividend_percentages[k];
   }
   const size_t o_d = put(dv.data(), sizeof(double) * dv.size());
+  size_t o_sg = 0, o_so = 0;
+  if (use_split) {
+    o_sg = put(sched.segs.data(), sizeof(HadiSegment) * sched.segs.size());
+    o_so = put(sched.off.data(), sizeof(int) * sched.off.size());
+  }
   cudaError_t e = cudaMemcpyAsync(d_stage, h_stage, off, cudaMemcpyHostToDevice, ctx->stream);
   ctx->h2d_bytes += (long long)off;
   if (e != cudaSuccess) {
@@ -595,6 +719,20 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
   L.out_U = nullptr;
   L.out_lam = nullptr;
   L.scheme = num->scheme;
+  L.segs = nullptr; L.seg_off = nullptr; L.hand_state = nullptr; L.hand_data = nullptr;
+  if (use_split) {
+    int* hs = (int*)take(sizeof(int) * (size_t)sched.n_hand, false);
+    double* hd = (double*)take(sizeof(double) * 2 * (size_t)P * (size_t)sched.n_hand, false);
+    if (!hs || !hd) {
+      release_all();
+      return HADI_ERR_NOMEM;
+    }
+    L.segs = (const HadiSegment*)(d_stage + o_sg);
+    L.seg_off = (const int*)(d_stage + o_so);
+    L.hand_state = hs;
+    L.hand_data = hd;
+    b->n_hand = sched.n_hand;
+  }
   L.dbg_step = L.dbg_phase = 0;
   if (const char* ds = getenv("HADI_DEBUG_STOP")) sscanf(ds, "%d:%d", &L.dbg_step, &L.dbg_phase);
   L.prof = (long long*)take(sizeof(long long) * (8 * (size_t)b->grid_ctas + 1), false);
@@ -617,6 +755,10 @@ int hadi_batch_launch(hadi_batch* b) {
   cudaSetDevice(ctx->device);
   cudaError_t e = cudaMemsetAsync(b->L.counter, 0, sizeof(int), ctx->stream);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "memset");
+  if (b->n_hand > 0) {
+    e = cudaMemsetAsync(b->L.hand_state, 0, sizeof(int) * (size_t)b->n_hand, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "memset");
+  }
   cudaEventRecord(b->ev0, ctx->stream);
   if (b->n_items > 0) {
     const int rc = hadi_launch_douglas(b->L, b->plan, b->grid_ctas, ctx->stream);

@@ -107,9 +107,11 @@ struct HadiCoopFeed : HadiDirectFeed {
 template <class F> struct hadi_is_coop { static constexpr bool value = false; };
 template <> struct hadi_is_coop<HadiCoopFeed> { static constexpr bool value = true; };
 
+// n0..n1: the time steps to run (1..N for a whole solve); hin: state to resume from (nullptr: start from the payoff)
 template <int NT, int M1, int M2, bool EXACT, class Feed>
 __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiItem& it, HadiView& w, Feed& feed,
-                                                int tid, long long* tacc, long long& tlast) {
+                                                int tid, long long* tacc, long long& tlast, int n0, int n1,
+                                                const double* hin) {
   const int m1 = M1 ? M1 : L.m1, m2 = M2 ? M2 : L.m2;
   const double* sg = L.s_pool + it.s_off;
   const double* vg = L.v_pool + it.v_off;
@@ -119,9 +121,6 @@ __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiI
   unsigned bad = 0;
 
   hadi_phase_tables(it, w, sg, vg, tid, NT);
-#ifdef HADI_PFW
-  if (tid == 0) w.divk[w.n1 - 1] = 0;   // chunk counter of the L1 warm-up warp (spare word behind the dividend indices)
-#endif
   if constexpr (hadi_is_coop<Feed>::value && M1 > 0) {
     // staged / consumed block counters of the co-operative S1 (hadi_phases_fast.cuh)
     if (tid < 2 * hadi_co_warps(M2))
@@ -137,16 +136,27 @@ __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiI
     asm volatile("fence.proxy.async;" ::: "memory");
   }
   __syncthreads();  // the A2 assembly keeps scratch tables in Y: finish it before Y is initialised
-  // initial condition U = payoff (the reference's U_0 input array), lambda = 0
+  // initial condition U = payoff (the reference's U_0 input array), lambda = 0 — or the state another CTA
+  // left after step n0 - 1 (split schedule)
   {
     const HadiMap mp = hadi_map(m1, m2, tid, NT);
     if (mp.active) {
       const double pay = hadi_ti(w, TI_PAY)[mp.i];
       for (int j = mp.j0; j < mp.j1; ++j) {
-        w.U[j * w.ld + mp.i] = pay;
-        if (it.style == 1) {
-          hadi_lam_st(&w.lam[j * w.ld + mp.i], 0.0);
-          w.Y[j * w.ld + mp.i] = 0.0;   // phase E reads lambda from Y
+        if (hin == nullptr) {
+          w.U[j * w.ld + mp.i] = pay;
+          if (it.style == 1) {
+            hadi_lam_st(&w.lam[j * w.ld + mp.i], 0.0);
+            w.Y[j * w.ld + mp.i] = 0.0;   // phase E reads lambda from Y
+          }
+        } else {
+          const size_t p = (size_t)j * (m1 + 1) + mp.i;
+          w.U[j * w.ld + mp.i] = __ldcg(hin + p);
+          if (it.style == 1) {
+            const double lm = __ldcg(hin + (size_t)w.P + p);
+            hadi_lam_st(&w.lam[j * w.ld + mp.i], lm);
+            w.Y[j * w.ld + mp.i] = lm;
+          }
         }
       }
     }
@@ -161,7 +171,9 @@ __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiI
 
   int div_cur = 0;
   bool stopped = false;
-  for (int n = 1; n <= it.N; ++n) {
+  if (it.nd > 0)   // dividend queue position after the steps another CTA ran
+    for (int n = 1; n < n0; ++n) hadi_dividend_at(n, it.dt, it.nd, L.div_dates, div_cur);
+  for (int n = n0; n <= n1; ++n) {
     if (it.nd > 0) {
       const int hit = hadi_dividend_at(n, it.dt, it.nd, L.div_dates, div_cur);
       if (hit >= 0) {  // uniform across the CTA
@@ -391,15 +403,53 @@ __global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch
   }
   __syncthreads();
 
+  // Work source: whole items pulled from a global counter, or (split schedule) this CTA's static list of
+  // segments — McNaughton's wrap-around rule on the host cuts the one solve that straddles the end of a CTA's
+  // share of the batch in two, so that every CTA finishes at the same time instead of after a whole number of
+  // solves (hadi_host.cpp: build_split_schedule).
+  const bool split = (L.segs != nullptr) && !GLOBAL && FEED != 1 && FEED != 4;
+  int seg_q = split ? L.seg_off[blockIdx.x] : 0;
+  const int seg_end = split ? L.seg_off[blockIdx.x + 1] : 0;
   for (;;) {
-    if (tid == 0) s_item = atomicAdd(L.counter, 1);
-    __syncthreads();
-    const int item = s_item;
-    if (item >= L.n_items) break;
-    const HadiItem it = L.items[item];
+    HadiSegment sg;
+    if (split) {
+      if (seg_q >= seg_end) break;
+      sg = L.segs[seg_q++];
+    } else {
+      if (tid == 0) s_item = atomicAdd(L.counter, 1);
+      __syncthreads();
+      sg.item = s_item;
+      if (sg.item >= L.n_items) break;
+      sg.n0 = 1; sg.n1 = 0; sg.hin = -1; sg.hout = -1;
+    }
+    const HadiItem it = L.items[sg.item];
+    if (!split) sg.n1 = it.N;
     HADI_TICK(0)
-    // fast pass; if any guarded division left its range (never observed on option data), the item is
-    // re-solved with IEEE divisions so that the published value is exact in every case
+    // state left by the CTA that ran steps 1..n0-1: wait for it (bounded: after two seconds, or if that CTA's
+    // guarded divisions left their range, this CTA solves the item from the payoff instead)
+    bool whole_exact = false;
+    const double* hin = nullptr;
+    if (sg.hin >= 0) {
+      if (tid == 0) {
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        int st;
+        for (;;) {
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(st) : "l"(L.hand_state + sg.hin) : "memory");
+          if (st != HADI_HAND_PENDING) break;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+          if (t1 - t0 > 2000000000ull) { st = HADI_HAND_BAD; break; }
+          __nanosleep(200);
+        }
+        s_item = st;
+      }
+      __syncthreads();
+      if (s_item == HADI_HAND_READY) hin = L.hand_data + (size_t)sg.hin * 2 * (size_t)w.P;
+      else whole_exact = true;
+      __syncthreads();
+    }
+    // fast pass; if any guarded division left its range (never observed on option data at these grids), the
+    // item is re-solved with IEEE divisions so that the published value is exact in every case
     bool cs_done = false;
     if constexpr (GLOBAL) {
       if (L.scheme == 1) {
@@ -409,17 +459,46 @@ __global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch
     }
     if (!cs_done) {
 #ifdef HADI_FORCE_EXACT
-      hadi_solve_item<NT, M1, M2, true>(L, it, w, feed, tid, tacc, tlast);
+      if (!whole_exact) hadi_solve_item<NT, M1, M2, true>(L, it, w, feed, tid, tacc, tlast, sg.n0, sg.n1, hin);
 #else
+      if (!whole_exact) {
 #ifdef HADI_NO_RERUN   /* timing experiments only */
-      if (hadi_solve_item<NT, M1, M2, false>(L, it, w, feed, tid, tacc, tlast) && L.n_items < 0) {
+        whole_exact = hadi_solve_item<NT, M1, M2, false>(L, it, w, feed, tid, tacc, tlast, sg.n0, sg.n1, hin) && L.n_items < 0;
 #else
-      if (hadi_solve_item<NT, M1, M2, false>(L, it, w, feed, tid, tacc, tlast)) {
+        whole_exact = hadi_solve_item<NT, M1, M2, false>(L, it, w, feed, tid, tacc, tlast, sg.n0, sg.n1, hin);
 #endif
-        if (tid == 0 && L.prof != nullptr) atomicAdd((unsigned long long*)&L.prof[(size_t)gridDim.x * 8], 1ULL);
-        hadi_solve_item<NT, M1, M2, true>(L, it, w, feed, tid, tacc, tlast);
       }
 #endif
+      if (L.dbg_step == -7) whole_exact = true;   // test hook (HADI_DEBUG_STOP=-7:0): treat every fast pass as out of range
+      if (whole_exact) {
+        if (tid == 0 && L.prof != nullptr) atomicAdd((unsigned long long*)&L.prof[(size_t)gridDim.x * 8], 1ULL);
+        // only the CTA that holds the last steps publishes: it re-solves the whole item
+        if (sg.hout < 0) hadi_solve_item<NT, M1, M2, true>(L, it, w, feed, tid, tacc, tlast, 1, it.N, nullptr);
+      }
+    }
+
+    if (sg.hout >= 0) {
+      // hand the state after step n1 to the CTA that runs the remaining steps
+      double* ho = L.hand_data + (size_t)sg.hout * 2 * (size_t)w.P;
+      if (!whole_exact) {
+        const HadiMap mp = hadi_map(m1, m2, tid, NT);
+        if (mp.active) {
+          for (int j = mp.j0; j < mp.j1; ++j) {
+            const size_t p = (size_t)j * (m1 + 1) + mp.i;
+            __stcg(ho + p, w.U[j * w.ld + mp.i]);
+            if (it.style == 1) __stcg(ho + (size_t)w.P + p, w.Y[j * w.ld + mp.i]);   // lambda sits in Y between steps
+          }
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        const int st = whole_exact ? HADI_HAND_BAD : HADI_HAND_READY;
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(L.hand_state + sg.hout), "r"(st) : "memory");
+      }
+      __syncthreads();
+      HADI_TICK(6)
+      continue;
     }
 
     if (tid == 0) hadi_publish(L, it, w);

@@ -7,6 +7,16 @@
 #define HADI_LEAN 1   /* grid-specialised variants keep only the TI_CORE per-column tables in shared memory */
 #endif
 
+// One entry of a CTA's static work list (split schedule): time steps n0..n1 (1-based, inclusive) of items[item].
+// A solve cut in two hands its state (U, lambda) from the CTA that ran steps 1..k to the CTA that runs
+// k+1..N through hand-off slot `hout` of the first == `hin` of the second (-1: none).
+struct HadiSegment {
+  int item, n0, n1, hin, hout, pad0, pad1, pad2;
+};
+#define HADI_HAND_PENDING 0
+#define HADI_HAND_READY 1
+#define HADI_HAND_BAD 2      /* a guarded division left its range: the final segment re-solves the whole item with IEEE '/' */
+
 struct HadiLaunch {
   int m1, m2, ld, n1, n2, pj;
   int n_items;
@@ -28,6 +38,11 @@ struct HadiLaunch {
   long long* prof;           // optional [gridDim.x][8] phase cycle counters (HADI_PHASE_TIMING builds only)
   int dbg_step, dbg_phase;   // HADI_DEBUG_STOP builds only: end every item after phase dbg_phase of step dbg_step
   int scheme;                // 0 Douglas, 1 Craig-Sneyd (global-state kernel only)
+  // split schedule (nullptr: CTAs pull whole items from `counter`): CTA b runs segs[seg_off[b] .. seg_off[b+1])
+  const HadiSegment* segs;
+  const int* seg_off;        // [gridDim.x + 1]
+  int* hand_state;           // [n_hand] HADI_HAND_* (zeroed before launch)
+  double* hand_data;         // [n_hand][2 * P]: U then lambda, natural layout
 };
 
 // Kernel variant chosen for a grid shape (hadi_kernel.cu).

@@ -34,7 +34,7 @@ EXPORTS = [
     "hadi_batch_phase_cycles", "hadi_bs_vega", "hadi_bs_implied_vol", "hadi_bs_implied_vol_bisect",
     "hadi_dividend_adjusted_spot", "hadi_market_prices", "hadi_implied_vols", "hadi_write_calibration_csv",
     "hadi_batch_create_ex", "hadi_batch_values_per_item", "hadi_jacobian_assemble_ex", "hadi_jacobian_v0_weight",
-    "hadi_jacobian_batch_ex", "hadi_calibrate_ex",
+    "hadi_jacobian_batch_ex", "hadi_calibrate_ex", "hadi_plan_schedule",
 ]
 
 
@@ -147,6 +147,7 @@ def lib():
         L.hadi_calibrate_ex.argtypes = [C.c_void_p, C.POINTER(Model), C.POINTER(Numerics), C.c_int,
                                         C.POINTER(Point), _dp, C.POINTER(LmOptions), C.POINTER(JacobianOptions),
                                         C.POINTER(Comm), C.POINTER(LmResult)]
+        L.hadi_plan_schedule.argtypes = [C.c_int, _ip, C.c_int, C.c_double, C.c_int, _ip, _ip, _dp]
         L.hadi_bs_vega.argtypes = [C.c_double] * 5
         L.hadi_bs_vega.restype = C.c_double
         L.hadi_bs_implied_vol.argtypes = [C.c_double] * 7
@@ -333,6 +334,23 @@ def jacobian_assemble(values, eps):
     if rc != OK:
         raise HadiError(rc)
     return J, base
+
+
+def plan_schedule(time_steps, slots, setup=1.5):
+    """(segments [(item, n0, n1, hin, hout)], slot_off, heaviest load in steps) of the split schedule; ([], None, 0)
+    when nothing is cut."""
+    ts = np.ascontiguousarray(time_steps, dtype=np.int32)
+    cap = 2 * ts.size + slots + 8
+    seg = np.zeros(5 * cap, dtype=np.int32)
+    off = np.zeros(slots + 1, dtype=np.int32)
+    hv = C.c_double(0.0)
+    rc = lib().hadi_plan_schedule(ts.size, ts.ctypes.data_as(_ip), slots, setup, cap, seg.ctypes.data_as(_ip),
+                                  off.ctypes.data_as(_ip), C.byref(hv))
+    if rc < 0:
+        raise HadiError(rc)
+    if rc == 0:
+        return [], None, 0.0
+    return [tuple(int(x) for x in seg[5 * q:5 * q + 5]) for q in range(rc)], off, hv.value
 
 
 def jacobian_v0_weight(m2, V0, eps_v0):

@@ -476,3 +476,37 @@ def test_lm_with_interpolated_v0_column(hadi, ctx):
     jac_calls = itp["iterations"]
     assert itp["pde_solves"] == jac_calls * 5 * n + (jac_calls - 1) * n
     assert itp["final_error"] <= 2.0 * ref["final_error"] + tol
+
+
+def test_split_schedule_is_bit_equal_to_whole_solves(hadi, ctx, oracle, monkeypatch):
+    """Batches larger than the persistent grid run on the split schedule: solves cut in two hand U and lambda
+    from one CTA to another through L2.  Same bits as whole solves (HADI_NO_SPLIT=1), also across dividend dates
+    and exercise updates, on the grid-specialised and the run-time-dimension kernels — and when every fast pass
+    is declared out of range, so that the CTA holding the last steps re-solves the item with IEEE divisions."""
+    mdl = hadi.make_model(**BASE)
+    cases = [(100, 50, 620, 12, hadi.AMERICAN, DIVS), (50, 25, 930, 9, hadi.AMERICAN, DIVS), (64, 32, 500, 7, hadi.EUROPEAN, None)]
+    for m1, m2, n, N, style, dv in cases:
+        num = hadi.make_numerics(m1, m2, 0.8, style, hadi.CALL, hadi.DOUGLAS, dv)
+        Ns = [N + (k % 4) for k in range(n)]
+        strikes = [75.0 + 50.0 * k / n for k in range(n)]
+        pts, _ = hadi.make_points(strikes, 1.0, Ns)
+        monkeypatch.delenv("HADI_NO_SPLIT", raising=False)
+        monkeypatch.delenv("HADI_DEBUG_STOP", raising=False)
+        split = ctx.price_batch(mdl, num, pts, n, want_U=(m1 == 50), want_lambda=(m1 == 50))
+        monkeypatch.setenv("HADI_NO_SPLIT", "1")
+        whole = ctx.price_batch(mdl, num, pts, n, want_U=(m1 == 50), want_lambda=(m1 == 50))
+        monkeypatch.delenv("HADI_NO_SPLIT")
+        assert np.array_equal(split["prices"], whole["prices"])
+        if m1 == 50:
+            assert np.array_equal(split["U"], whole["U"]) and np.array_equal(split["lambda"], whole["lambda"])
+        monkeypatch.setenv("HADI_DEBUG_STOP", "-7:0")
+        exact = ctx.price_batch(mdl, num, pts, n)
+        monkeypatch.delenv("HADI_DEBUG_STOP")
+        assert np.array_equal(exact["prices"], whole["prices"])
+        for k in (0, n // 3, n - 1):
+            o = oracle.solve(strikes[k], Ns[k], 1.0 / Ns[k], m1=m1, m2=m2, theta=0.8, style=style, divs=dv,
+                             payoff_put=0, want_U=False, want_lambda=False, **BASE)
+            assert split["prices"][k] == o["price"]
+    # the schedule really was cut
+    segs, _, _ = hadi.plan_schedule(sorted([12 + (k % 4) for k in range(620)], reverse=True), 296)
+    assert any(s[3] >= 0 for s in segs)

@@ -191,3 +191,53 @@ def test_jacobian_assembly_of_every_mode(hadi):
     pts, n3 = hadi.make_points([90.0, 100.0], [1.0, 2.0], [20, 40])
     assert hadi.item_costs(num, pts, n3, hadi.MODE_JACOBIAN_INTERP).size == 10
     assert hadi.item_costs(num, pts, n3, hadi.MODE_JACOBIAN_CENTRAL).size == 22
+
+
+@pytest.mark.parametrize("case", ["config2", "mixed", "barely", "chain", "tiny_steps"])
+def test_split_schedule_covers_every_step_once(hadi, case):
+    """The split schedule of batches larger than the persistent grid (McNaughton's wrap-around rule): every time
+    step of every solve appears exactly once, a solve is cut at most once, the first steps of a cut solve open
+    the list of the CTA after the one its last steps close, hand-off slots pair up, and the heaviest CTA
+    carries (nearly) total / slots instead of a whole number of solves."""
+    ts, slots = dict(config2=([50] * 500, 296), mixed=(sorted([20 + (i % 3) * 5 for i in range(1000)], reverse=True), 444),
+                     barely=([50] * 297, 296), chain=(sorted([max(20, int(20 * t)) for t in (0.25, 0.5, 1, 2)] * 2500,
+                                                             reverse=True), 296),
+                     tiny_steps=([4] * 40, 16))[case]
+    segs, off, heaviest = hadi.plan_schedule(ts, slots)
+    if case == "tiny_steps":
+        assert segs == []   # solves of fewer than six steps are never cut: the CTAs pull whole items
+        return
+    assert segs, "a batch larger than the grid must be cut"
+    assert off[0] == 0 and off[slots] == len(segs) and all(off[b] <= off[b + 1] for b in range(slots))
+    slot_of = {}
+    for b in range(slots):
+        for q in range(off[b], off[b + 1]):
+            slot_of[q] = b
+    steps = [[] for _ in ts]
+    producers, consumers = {}, {}
+    for q, (item, n0, n1, hin, hout) in enumerate(segs):
+        assert 1 <= n0 <= n1 <= ts[item]
+        steps[item].append((n0, n1, q))
+        if hout >= 0:
+            assert n0 == 1 and n1 < ts[item] and hout not in producers
+            producers[hout] = q
+            assert q == off[slot_of[q]], "the first steps of a cut solve open their CTA's list"
+        if hin >= 0:
+            assert n0 > 1 and n1 == ts[item] and hin not in consumers
+            consumers[hin] = q
+            assert q == off[slot_of[q] + 1] - 1, "the last steps of a cut solve close their CTA's list"
+    assert sorted(producers) == sorted(consumers) == list(range(len(producers)))
+    for h, qp in producers.items():
+        qc = consumers[h]
+        assert segs[qp][0] == segs[qc][0] and segs[qp][2] + 1 == segs[qc][1]
+        assert slot_of[qp] == slot_of[qc] + 1
+    for item, parts in enumerate(steps):
+        parts.sort()
+        assert len(parts) in (1, 2) and parts[0][0] == 1 and parts[-1][1] == ts[item]
+        if len(parts) == 2:
+            assert parts[0][1] + 1 == parts[1][0]
+    ideal = (sum(ts) + 1.5 * len(ts)) / slots
+    whole = -(-len(ts) // slots) * (max(ts) + 1.5)
+    assert heaviest <= max(1.06 * ideal + 4.0, max(ts) + 1.5) and heaviest <= whole
+    # nothing to cut when every solve has its own CTA
+    assert hadi.plan_schedule([50] * 200, 296)[0] == []
