@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -48,6 +49,17 @@ struct hadi_ctx {
   // strikes dozens of times; the reference likewise builds its GridViews once, before the loop).
   std::map<std::tuple<int, uint64_t, uint64_t>, std::shared_ptr<std::vector<double>>> s_cache;
   std::map<int, std::shared_ptr<std::vector<double>>> v_base;  // d*sinh(j*d_eta) per m2
+  // Device-resident s-grids: a strike's grid is uploaded once and stays in HBM for the life of the context
+  // (an option chain is re-priced many times with the same strikes: every LM iteration, every bench step), so
+  // a steady-state call moves only the item descriptors.  One allocation that never moves: prepared batches keep
+  // pointing into it.  When it is full, batches carry their grids with them as before.
+  struct DevGrid { int off, idx_s; };
+  double* d_spool = nullptr;
+  size_t spool_cap = 0, spool_used = 0;   // doubles
+  bool spool_tried = false;
+  std::map<std::tuple<int, uint64_t, uint64_t>, DevGrid> s_dev;
+  // kernel plans per (m1, m2, scheme, few items, forced variant): the occupancy queries cost tens of microseconds
+  std::map<std::tuple<int, int, int, int, std::string>, std::pair<int, HadiPlan>> plans;
 };
 
 struct hadi_batch {
@@ -329,6 +341,7 @@ void hadi_destroy(hadi_ctx* ctx) {
     else
       cudaFree(b.p);
   }
+  if (ctx->d_spool) cudaFree(ctx->d_spool);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -506,7 +519,15 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
   const int m1 = g.m1, m2 = g.m2;
   const int P = (m1 + 1) * (m2 + 1);
   HadiPlan plan;
-  {
+  const char* forced_variant = getenv("HADI_FORCE_VARIANT");
+  const int n_it_plan = (item_end < 0 ? n * n_columns(mode) : item_end) - item_begin;
+  const auto plan_key = std::make_tuple(num->m1, num->m2, num->scheme,
+                                        (int)(n_it_plan * HADI_CLUSTER <= 148 && num->num_dividends == 0),
+                                        std::string(forced_variant ? forced_variant : ""));
+  const auto plan_hit = ctx->plans.find(plan_key);
+  if (plan_hit != ctx->plans.end() && plan_hit->second.first == 0) {
+    plan = plan_hit->second.second;
+  } else {
     const bool cs = num->scheme == HADI_CRAIG_SNEYD;
     // few large solves: spread each over a thread-block cluster (needs the global working set; the dividend
     // jump keeps per-CTA tables and stays on the one-CTA-per-solve kernels)
@@ -523,6 +544,7 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
     }
     if (prc < 0) return fail(ctx, HADI_ERR_SMEM, "grid too large: m1+1 <= 1024 and the coefficient tables must fit shared memory");
     if (prc > 0) return cuda_fail(ctx, (cudaError_t)prc, "kernel plan");
+    ctx->plans[plan_key] = std::make_pair(0, plan);
   }
 
   std::unique_ptr<hadi_batch> b(new hadi_batch());
@@ -536,6 +558,28 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
   std::vector<HadiItem> items(n_items);
   std::vector<double> s_pool, v_pool, e_pool;
   std::map<std::pair<uint64_t, uint64_t>, int> s_index;       // (K, S0) -> offset
+  // device-resident grid pool: usable when the grids this batch adds still fit
+  std::map<std::tuple<int, uint64_t, uint64_t>, hadi_ctx::DevGrid> pending;   // grids this call uploads
+  bool use_dev_pool = false;
+  if (!getenv("HADI_NO_GRID_CACHE")) {
+    if (!ctx->spool_tried) {
+      ctx->spool_tried = true;
+      const size_t cap = (size_t)4 << 20;   // 4 Mi doubles = 32 MiB: ~41 000 grids of 101 nodes
+      if (cudaMalloc((void**)&ctx->d_spool, cap * sizeof(double)) == cudaSuccess) ctx->spool_cap = cap;
+      else { ctx->d_spool = nullptr; cudaGetLastError(); }
+    }
+    if (ctx->d_spool) {
+      size_t need = 0;
+      std::map<std::tuple<int, uint64_t, uint64_t>, char> seen;
+      const int nc_ = n_columns(mode);
+      const int k0 = item_begin / nc_, k1 = n_items > 0 ? (item_end - 1) / nc_ : k0 - 1;
+      for (int k = k0; k <= k1; ++k) {
+        const auto dkey = std::make_tuple(m1, bits(points[k].strike), bits(model->S0));
+        if (ctx->s_dev.find(dkey) == ctx->s_dev.end() && seen.emplace(dkey, 1).second) need += (size_t)m1 + 1;
+      }
+      use_dev_pool = ctx->spool_used + need <= ctx->spool_cap;
+    }
+  }
   std::map<std::pair<uint64_t, int>, int> e_index;            // (dt, N) -> offset
   // three v-grids at most: V0, V0 + eps (src/jacobian_computation.cpp:339) and, for central differences, V0 - eps
   v_pool.resize((size_t)3 * (m2 + 1));
@@ -586,21 +630,38 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
     it.style = num->style;
     it.payoff = num->payoff;
     it.nd = num->num_dividends;
-    auto skey = std::make_pair(bits(pt.strike), bits(model->S0));
-    auto sit = s_index.find(skey);
-    const double* sg;
-    if (sit == s_index.end()) {
-      auto gs = s_grid(ctx, m1, pt.strike, model->S0);
-      const int off = (int)s_pool.size();
-      s_pool.insert(s_pool.end(), gs->begin(), gs->end());
-      s_index.emplace(skey, off);
-      it.s_off = off;
+    if (use_dev_pool) {
+      const auto dkey = std::make_tuple(m1, bits(pt.strike), bits(model->S0));
+      auto dit = ctx->s_dev.find(dkey);
+      if (dit == ctx->s_dev.end()) {
+        dit = pending.find(dkey);
+        if (dit == pending.end()) {
+          auto gs = s_grid(ctx, m1, pt.strike, model->S0);
+          hadi_ctx::DevGrid dg;
+          dg.off = (int)(ctx->spool_used + s_pool.size());
+          dg.idx_s = find_node(gs->data(), m1 + 1, model->S0);
+          if (dg.idx_s < 0) return fail(ctx, HADI_ERR_GRID, "S0 is not a node of the s-grid");
+          s_pool.insert(s_pool.end(), gs->begin(), gs->end());
+          dit = pending.emplace(dkey, dg).first;
+        }
+      }
+      it.s_off = dit->second.off;
+      it.idx_s = dit->second.idx_s;
     } else {
-      it.s_off = sit->second;
+      auto skey = std::make_pair(bits(pt.strike), bits(model->S0));
+      auto sit = s_index.find(skey);
+      if (sit == s_index.end()) {
+        auto gs = s_grid(ctx, m1, pt.strike, model->S0);
+        const int off = (int)s_pool.size();
+        s_pool.insert(s_pool.end(), gs->begin(), gs->end());
+        s_index.emplace(skey, off);
+        it.s_off = off;
+      } else {
+        it.s_off = sit->second;
+      }
+      it.idx_s = find_node(s_pool.data() + it.s_off, m1 + 1, model->S0);
+      if (it.idx_s < 0) return fail(ctx, HADI_ERR_GRID, "S0 is not a node of the s-grid");
     }
-    sg = s_pool.data() + it.s_off;
-    it.idx_s = find_node(sg, m1 + 1, model->S0);
-    if (it.idx_s < 0) return fail(ctx, HADI_ERR_GRID, "S0 is not a node of the s-grid");
     it.v_off = (col == 5) ? (m2 + 1) : (col == 10) ? 2 * (m2 + 1) : 0;
     it.idx_v = (col == 5) ? idx_v1 : (col == 10) ? idx_v2 : idx_v0;
     it.aux = br_lo | (br_hi << 16);
@@ -695,16 +756,26 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
   }
   cudaError_t e = cudaMemcpyAsync(d_stage, h_stage, off, cudaMemcpyHostToDevice, ctx->stream);
   ctx->h2d_bytes += (long long)off;
+  if (e == cudaSuccess && use_dev_pool && !s_pool.empty()) {
+    // grids seen for the first time: into the context's pool, ahead of the kernel on the same stream
+    e = cudaMemcpyAsync(ctx->d_spool + ctx->spool_used, h_stage + o_s, sizeof(double) * s_pool.size(),
+                        cudaMemcpyHostToDevice, ctx->stream);
+    ctx->h2d_bytes += (long long)(sizeof(double) * s_pool.size());
+  }
   if (e != cudaSuccess) {
     release_all();
     return cuda_fail(ctx, e, "H2D");
+  }
+  if (use_dev_pool) {
+    ctx->spool_used += s_pool.size();
+    ctx->s_dev.insert(pending.begin(), pending.end());
   }
 
   HadiLaunch& L = b->L;
   L.m1 = m1; L.m2 = m2; L.ld = g.ld; L.n1 = g.n1; L.n2 = g.n2; L.pj = g.pj;
   L.n_items = n_items;
   L.items = (const HadiItem*)(d_stage + o_items);
-  L.s_pool = (const double*)(d_stage + o_s);
+  L.s_pool = use_dev_pool ? ctx->d_spool : (const double*)(d_stage + o_s);
   L.v_pool = (const double*)(d_stage + o_v);
   L.e_pool = (const double*)(d_stage + o_e);
   L.nd = nd;
@@ -842,8 +913,11 @@ static int run_items(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics
                      const hadi_point* points, int mode, const double* eps5, int begin, int end, double* values,
                      double* U_out, double* lam_out, float* ms) {
   hadi_batch* b = nullptr;
+  static const bool host_timing = getenv("HADI_HOST_TIMING") != nullptr;   // development aid: stage times on stderr
+  const auto ht0 = std::chrono::steady_clock::now();
   int rc = hadi_batch_create_ex(ctx, model, num, n, points, mode, eps5, begin, end, &b);
   if (rc != HADI_OK) return rc;
+  const auto ht1 = std::chrono::steady_clock::now();
   const size_t P = (size_t)(num->m1 + 1) * (size_t)(num->m2 + 1);
   int idU = -1, idL = -1;
   if (U_out) {
@@ -868,6 +942,14 @@ static int run_items(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics
     if (cudaMemcpy(lam_out, b->L.out_lam, sizeof(double) * P * (size_t)b->n_items, cudaMemcpyDeviceToHost) != cudaSuccess)
       rc = cuda_fail(ctx, cudaGetLastError(), "D2H lambda");
   if (rc == HADI_OK && ms) hadi_batch_elapsed_ms(b, ms);
+  if (host_timing && rc == HADI_OK) {
+    const auto ht2 = std::chrono::steady_clock::now();
+    float kms = 0.f;
+    hadi_batch_elapsed_ms(b, &kms);
+    fprintf(stderr, "[hadi] items %d: create %.1f us, launch+kernel+fetch %.1f us (kernel %.1f us)\n", b->n_items,
+            std::chrono::duration<double, std::micro>(ht1 - ht0).count(),
+            std::chrono::duration<double, std::micro>(ht2 - ht1).count(), kms * 1e3);
+  }
   hadi_batch_destroy(b);
   return rc;
 }

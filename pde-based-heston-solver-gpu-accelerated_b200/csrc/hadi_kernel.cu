@@ -785,6 +785,14 @@ int hadi_douglas_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj
 
 int hadi_launch_douglas(const HadiLaunch& L, const HadiPlan& plan, int grid_ctas, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  // the run-time-dimension kernels serve many grid shapes and plans are cached by the host layer: the dynamic
+  // shared-memory limit of the function must be the one of THIS plan, not of the plan made last
+  {
+    const void* fn = plan.variant == kClusterVariant ? (const void*)hadi_cluster_kernel<kClusterThreads>
+                                                     : variants()[plan.variant].fn;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes);
+    if (e != cudaSuccess) return (int)e;
+  }
   switch (plan.variant) {
 #define X(id, nt, minb, a, b, r, g) \
   case id:                          \

@@ -510,3 +510,32 @@ def test_split_schedule_is_bit_equal_to_whole_solves(hadi, ctx, oracle, monkeypa
     # the schedule really was cut
     segs, _, _ = hadi.plan_schedule(sorted([12 + (k % 4) for k in range(620)], reverse=True), 296)
     assert any(s[3] >= 0 for s in segs)
+
+
+def test_device_resident_grid_pool(hadi, monkeypatch):
+    """Strike grids are uploaded once per context and stay in HBM: the second pricing of a chain moves only the
+    item descriptors, a chain with new strikes adds only its new grids, and the prices are the ones a context
+    without the pool produces."""
+    mdl = hadi.make_model(**BASE)
+    num = hadi.make_numerics(100, 50, 0.8, hadi.AMERICAN, hadi.CALL, hadi.DOUGLAS, DIVS)
+    strikes = [80.0 + 0.25 * k for k in range(160)]
+    pts, n = hadi.make_points(strikes, 1.0, 10)
+    c1 = hadi.Context(0)
+    h0, _ = c1.transfer_bytes()
+    a = c1.price_batch(mdl, num, pts, n)["prices"].copy()
+    h1, _ = c1.transfer_bytes()
+    b = c1.price_batch(mdl, num, pts, n)["prices"].copy()
+    h2, _ = c1.transfer_bytes()
+    grid_bytes = n * 101 * 8
+    assert (h1 - h0) - (h2 - h1) >= grid_bytes and (h2 - h1) < grid_bytes
+    pts2, n2 = hadi.make_points(strikes[:80] + [131.0, 132.0], 1.0, 10)
+    c = c1.price_batch(mdl, num, pts2, n2)["prices"].copy()
+    h3, _ = c1.transfer_bytes()
+    assert (h3 - h2) < (h2 - h1) + 3 * 101 * 8
+    c1.close()
+    monkeypatch.setenv("HADI_NO_GRID_CACHE", "1")
+    c2 = hadi.Context(0)
+    ref = c2.price_batch(mdl, num, pts, n)["prices"].copy()
+    ref2 = c2.price_batch(mdl, num, pts2, n2)["prices"].copy()
+    c2.close()
+    assert np.array_equal(a, ref) and np.array_equal(b, ref) and np.array_equal(c, ref2)
