@@ -344,9 +344,9 @@ __global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch
   const HadiSmemLayout lay = hadi_smem_layout(m1, m2, w.ld, w.n1, w.n2, w.pj, FEED == 1, GLOBAL, FEED == 4, M1 > 0);
   if constexpr (M1 > 0) w.nti = HADI_LEAN ? TI_CORE : TI_COUNT;
   char* sbase = reinterpret_cast<char*>(smem);
+  w.zmask = (L.n_items < 0) ? ~0u : 0u;   // a zero the compiler cannot fold
   if constexpr (FEED == 4) {
     w.co_pi = hadi_co_pi(m1);
-    w.zmask = (L.n_items < 0) ? ~0u : 0u;
     w.stg = reinterpret_cast<double*>(sbase + lay.ring);
   }
   double* scratch = L.scratch + (size_t)blockIdx.x * L.scratch_stride;
