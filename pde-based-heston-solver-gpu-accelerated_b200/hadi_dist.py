@@ -16,20 +16,42 @@ def slices(hadi, costs, world):
     return [hadi.partition(costs, world, r) for r in range(world)]
 
 
+_bufs = {}
+
+
 def allgather_values(mine, counts, dist=None, device=None):
-    """All-gather variable-length float64 slices in rank order (pads to the longest slice)."""
+    """All-gather variable-length float64 slices in rank order: one padded all_gather_into_tensor and one
+    device-to-host copy per call; the staging tensors are cached per (longest slice, world, device)."""
     import torch
 
     if dist is None:
         import torch.distributed as dist
     world = dist.get_world_size()
+    if not sum(counts):
+        return np.zeros(0)
     mx = max(max(counts), 1)
-    buf = torch.zeros(mx, dtype=torch.float64, device=device)
-    if len(mine):
-        buf[:len(mine)] = torch.as_tensor(np.asarray(mine, dtype=np.float64), device=device)
-    out = [torch.zeros(mx, dtype=torch.float64, device=device) for _ in range(world)]
-    dist.all_gather(out, buf)
-    return np.concatenate([out[r][:counts[r]].cpu().numpy() for r in range(world)]) if sum(counts) else np.zeros(0)
+    key = (mx, world, str(device))
+    if key not in _bufs:
+        pin = device is not None and torch.device(device).type == "cuda"
+        _bufs[key] = (torch.zeros(mx, dtype=torch.float64, pin_memory=pin),
+                      torch.zeros(mx, dtype=torch.float64, device=device),
+                      torch.zeros(world * mx, dtype=torch.float64, device=device),
+                      torch.zeros(world * mx, dtype=torch.float64, pin_memory=pin))
+    h_in, d_in, d_out, h_out = _bufs[key]
+    m = np.asarray(mine, dtype=np.float64)
+    if m.size:
+        h_in.numpy()[:m.size] = m
+    d_in.copy_(h_in, non_blocking=True)
+    if hasattr(dist, "all_gather_into_tensor") and d_out.device.type == "cuda":
+        dist.all_gather_into_tensor(d_out, d_in)
+    else:   # gloo (CPU tests)
+        parts = [d_out[r * mx:(r + 1) * mx] for r in range(world)]
+        dist.all_gather(parts, d_in)
+    h_out.copy_(d_out, non_blocking=True)
+    if d_out.device.type == "cuda":
+        torch.cuda.current_stream(d_out.device).synchronize()
+    full = h_out.numpy()
+    return np.concatenate([full[r * mx:r * mx + counts[r]] for r in range(world)])
 
 
 def solve_items_sharded(hadi, num, pts, n, mode, local_solve, rank, world, device=None, dist=None):
