@@ -183,6 +183,19 @@ def lm_calibration(hadi, ctx, comm=None):
             best = ms if best is None else min(best, ms)
         out[name] = {"wall_ms": round(best, 3), "gpu_ms": round(res["gpu_ms"], 3), "iterations": res["iterations"],
                      "pde_solves": res["pde_solves"], "converged": res["converged"]}
+    # opt-in: V0 column of the Jacobian interpolated on the base solve (5 solves per point; not the reference's
+    # trajectory — reported beside the parity run, never instead of it)
+    num = hadi.make_numerics(50, 25, THETA)
+    best = None
+    for rep in range(3):
+        t0 = time.perf_counter()
+        res = ctx.calibrate(hadi.make_model(**BASE), num, pts, n, market, 15, 0.1 * math.sqrt(n),
+                            0.1 * (1.0 + math.log(n)), comm=comm, jac_mode=hadi.MODE_JACOBIAN_INTERP)
+        ms = (time.perf_counter() - t0) * 1e3
+        best = ms if best is None else min(best, ms)
+    out["51x26_interpolated_v0_optin"] = {"wall_ms": round(best, 3), "gpu_ms": round(res["gpu_ms"], 3),
+                                          "iterations": res["iterations"], "pde_solves": res["pde_solves"],
+                                          "converged": res["converged"]}
     return out
 
 
