@@ -52,6 +52,33 @@ def _worker(rank, world, port, q):
     vals = hd.solve_items_sharded(hadi, num, pts, n, hadi.MODE_JACOBIAN, local_solve, rank, world, dist=dist)
     J, base = hadi.jacobian_assemble(vals, eps)
     delta = hadi.lm_update(J, np.linspace(-0.1, 0.1, n), 0.01)
+    # opt-in Jacobian with the V0 column interpolated on the base solve: 5 items per option, THREE values per
+    # item (price, U at the two v-rows bracketing V0 + eps on the S0 column) — the gather counts scale with it
+    lo, hi, wgt = hadi.jacobian_v0_weight(10, BASE["V0"], eps)
+
+    def local_solve_interp(b, e):
+        vals = []
+        for item in range(b, e):
+            k, col = divmod(item, 5)
+            m = dict(BASE)
+            if col == 1: m["kappa"] += eps
+            if col == 2: m["eta"] += eps
+            if col == 3: m["sigma"] += eps
+            if col == 4: m["rho"] += eps
+            o = O.solve(strikes[k], Ns[k], mats[k] / Ns[k], m1=20, m2=10, theta=0.8, want_U=True, want_lambda=False, **m)
+            sg, _ = hadi.grid(20, 10, strikes[k], BASE["S0"], BASE["V0"])
+            i_s = int(np.argmax(np.abs(sg - BASE["S0"]) < 1e-10))
+            U = np.asarray(o["U"]).reshape(11, 21)
+            vals += [o["price"], U[lo, i_s], U[hi, i_s]]
+        return np.array(vals)
+
+    vi = hd.solve_items_sharded(hadi, num, pts, n, hadi.MODE_JACOBIAN_INTERP, local_solve_interp, rank, world, dist=dist)
+    Ji, bi = hadi.jacobian_assemble_ex(vi, hadi.MODE_JACOBIAN_INTERP, eps, wgt)
+    full = local_solve_interp(0, 5 * n)
+    assert np.array_equal(vi, full) and np.array_equal(bi, base) and np.array_equal(Ji[:, :4], J[:, :4])
+    for k in range(n):
+        o = full[15 * k:15 * k + 3]
+        assert Ji[k, 4] == ((o[1] + wgt * (o[2] - o[1])) - o[0]) / eps
     q.put((rank, vals.tolist(), J.tolist(), base.tolist(), delta.tolist()))
     dist.barrier()
     dist.destroy_process_group()
