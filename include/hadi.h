@@ -19,6 +19,12 @@
  *                                       2692-2831, 3568-3716
  *   CalibrationPoint                    src/heston_calibration.cpp:2165-2171    hadi_point
  *   parallel_DO_solve                   src/device_solver.hpp:53                hadi_price_batch
+ *   Jacobian with the V0 column interpolated on the base solve (prototype)      hadi_jacobian_batch_ex,
+ *       src/device_solver.cpp:1725-1829                                         hadi_calibrate_ex (opt-in)
+ *   BlackScholes::call_vega / reverse_BS / reverse_BS_dic  src/bs.hpp:124-192   hadi_bs_vega, hadi_bs_implied_vol{,_bisect}
+ *   BlackScholes::generate_market_data{,_with_dividends}   src/bs.hpp:58-112    hadi_market_prices, hadi_dividend_adjusted_spot
+ *   implied-vol post-processing and CSV export of the LM drivers                hadi_implied_vols, hadi_write_calibration_csv
+ *       src/heston_calibration.cpp:436-511, 2853-2923
  *
  * Conventions
  *   - Plain C types only.  All pointers are HOST pointers unless the name ends in _dev.
