@@ -104,22 +104,42 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+_REF = None
+
+
+def ref_lib():
+    """oracle/_ref (the reference's own sources) with its league loop on ALL host cores.  torchrun exports
+    OMP_NUM_THREADS=1 to its children, so the thread count is set through the library, not the environment,
+    and the count reported is the one omp_get_max_threads() returns afterwards."""
+    global _REF
+    from oracle.reflib import RefLib, have_ref
+
+    if _REF is None and have_ref(omp=True):
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)   # before libgomp is loaded
+        R = RefLib(omp=True)
+        _REF = (R, R.set_threads(os.cpu_count() or 1))
+    return _REF
+
+
 def cpu_baseline(sample_factor=None):
     """The reference's own sources (oracle/_ref, OpenMP over options outside the reference code) on the
-    host cores, on a bounded sample of the same workload."""
-    from oracle.reflib import OracleLib, RefLib, have_ref
+    host cores, on a bounded sample of the same workload.  Timed: the reference entry point
+    (compute_base_prices_american_dividends) alone — the driver's problem set-up (grids, U_0, the 12-array
+    workspace) is outside the timed region, as it is outside the reference's own benchmark loops."""
+    from oracle.reflib import OracleLib
 
     cores = os.cpu_count() or 1
     # default: the whole 500-option step (about 20 s of CPU work: 41 ms per solve and core)
     n = NOPT if sample_factor is None else max(8, min(NOPT, sample_factor * cores))
     strikes = strikes_for(0)[:n]
-    if have_ref(omp=True):
-        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-        R = RefLib(omp=True)
+    ref = ref_lib()
+    if ref is not None:
+        R, cores = ref
         kind = "reference"
 
         def run():
-            return R.solve_batch(strikes, NSTEP, 1.0 / NSTEP, m1=M1, m2=M2, theta=THETA, style=1, divs=DIVS, **BASE)["prices"]
+            p = R.solve_batch(strikes, NSTEP, 1.0 / NSTEP, m1=M1, m2=M2, theta=THETA, style=1, divs=DIVS, **BASE)["prices"]
+            return p, R.last_compute_seconds()
     else:
         O = OracleLib()
         kind, cores = "port", 1
@@ -127,13 +147,23 @@ def cpu_baseline(sample_factor=None):
         strikes = strikes[:n]
 
         def run():
-            return O.price_batch(strikes, NSTEP, 1.0 / NSTEP, m1=M1, m2=M2, theta=THETA, style=1, divs=DIVS, **BASE)
+            t0 = time.perf_counter()
+            p = O.price_batch(strikes, NSTEP, 1.0 / NSTEP, m1=M1, m2=M2, theta=THETA, style=1, divs=DIVS, **BASE)
+            return p, time.perf_counter() - t0
     run()  # warm-up (page in, thread pool)
     t0 = time.perf_counter()
-    prices = run()
-    dt = time.perf_counter() - t0
+    prices, dt = run()
+    wall = time.perf_counter() - t0
     return {"value": n / dt, "unit": "solves/s", "cores": cores, "kind": kind,
-            "sample": "%d of the %d options of the step, %.2f s wall" % (n, NOPT, dt)}, prices, strikes
+            "sample": "%d of the %d options of the step: %.2f s in the reference entry point on %d threads "
+                      "(%.2f s wall with the driver's problem set-up)" % (n, NOPT, dt, cores, wall)}, prices, strikes
+
+
+def bench_config():
+    """`config` of the JSON line: identical keys and values on both arms."""
+    return {"workload": WORKLOAD, "options_per_gpu": NOPT, "grid": "101x51", "time_steps": NSTEP,
+            "l2": "256 MiB buffer written between timed iterations (L2 flush)",
+            "timing": "CUDA events around each launch on the launching stream, summed over the steps, max over ranks"}
 
 
 def run_reference(args):
@@ -152,7 +182,8 @@ def run_reference(args):
     line = {"metric": METRIC, "value": v, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": WORKLOAD, "note": "each step = bounded sample of the workload on the host cores"},
+            "config": bench_config(),
+            "reference_note": "each step = the whole 500-option workload on the host cores (reference entry point timed)",
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -160,15 +191,9 @@ def run_reference(args):
     return 0
 
 
-def lm_calibration(hadi, ctx, comm=None):
+def lm_calibration(hadi, ctx, comm=None, world=1, rank=0, dist=None):
     """BASELINE configs[2]: LM calibration to a 10-strike x 10-maturity synthetic European surface."""
-    mats = [1.0 + i * 0.25 if i < 8 else 3.0 + (i - 8) * 0.5 for i in range(10)]
-    K, T, N = [], [], []
-    for Tm in mats:
-        for s in range(10):
-            K.append(95.0 + 1.0 * s)
-            T.append(Tm)
-            N.append(max(20, int(Tm * 20)))
+    K, T, N = c3_surface()
     market = [hadi.bs_call(100.0, k, 0.025, 0.2, t) for k, t in zip(K, T)]
     pts, n = hadi.make_points(K, T, N)
     out = {}
@@ -182,7 +207,29 @@ def lm_calibration(hadi, ctx, comm=None):
             ms = (time.perf_counter() - t0) * 1e3
             best = ms if best is None else min(best, ms)
         out[name] = {"wall_ms": round(best, 3), "gpu_ms": round(res["gpu_ms"], 3), "iterations": res["iterations"],
-                     "pde_solves": res["pde_solves"], "converged": res["converged"]}
+                     "pde_solves": res["pde_solves"], "converged": res["converged"],
+                     "params": [repr(float(x)) for x in res["params"]], "final_error": repr(float(res["final_error"]))}
+        if world > 1:
+            # the same calibration on ONE GPU in the same run (rank 0; the others wait): strong-scaling efficiency
+            if rank == 0:
+                one = None
+                for rep in range(3):
+                    t0 = time.perf_counter()
+                    r1 = ctx.calibrate(hadi.make_model(**BASE), num, pts, n, market, 15, 0.1 * math.sqrt(n),
+                                       0.1 * (1.0 + math.log(n)), comm=None)
+                    ms = (time.perf_counter() - t0) * 1e3
+                    one = ms if one is None else min(one, ms)
+                out[name]["single_gpu_wall_ms"] = round(one, 3)
+                out[name]["strong_scaling_efficiency"] = round(one / (world * best), 4)
+                out[name]["equals_single_gpu"] = bool(r1["params"] == res["params"] and r1["final_error"] == res["final_error"])
+            dist.barrier()
+        try:   # golden trajectory of the reference itself (tests/golden/lm_more.json, oracle/make_golden.py more)
+            G = json.load(open(os.path.join(ROOT, "tests", "golden", "lm_more.json")))["config3_" + name]
+            out[name]["equals_reference"] = bool(out[name]["params"] == G["params"] and
+                                                 out[name]["final_error"] == G["final_error"] and
+                                                 res["iterations"] == G["iterations"])
+        except Exception:
+            out[name]["equals_reference"] = None
     # opt-in: V0 column of the Jacobian interpolated on the base solve (5 solves per point; not the reference's
     # trajectory — reported beside the parity run, never instead of it)
     num = hadi.make_numerics(50, 25, THETA)
@@ -199,12 +246,42 @@ def lm_calibration(hadi, ctx, comm=None):
     return out
 
 
+def c5_chain():
+    """SURVEY C5 exactly: K_i = 50 + 0.01 i, maturities cycling {0.25, 0.5, 1, 2}, N = max(20, int(20 T)),
+    European Douglas on the 101x51 grid."""
+    cyc = (0.25, 0.5, 1.0, 2.0)
+    K = [50.0 + 0.01 * i for i in range(10000)]
+    T = [cyc[i % 4] for i in range(10000)]
+    N = [max(20, int(20 * t)) for t in T]
+    return K, T, N
+
+
+def c3_surface():
+    """BASELINE configs[2] / SURVEY C3: 10 strikes x 10 maturities, market = Black-Scholes at 20 % vol."""
+    mats = [1.0 + i * 0.25 if i < 8 else 3.0 + (i - 8) * 0.5 for i in range(10)]
+    K, T, N = [], [], []
+    for Tm in mats:
+        for s in range(10):
+            K.append(95.0 + 1.0 * s)
+            T.append(Tm)
+            N.append(max(20, int(Tm * 20)))
+    return K, T, N
+
+
+def _digest(a):
+    import hashlib
+    import numpy as np
+
+    return hashlib.sha256((np.ascontiguousarray(a, dtype=np.float64) + 0.0).tobytes()).hexdigest()[:16]
+
+
 def sharded_chains(hadi, ctx, torch, dev, rank, world, dist):
-    """BASELINE target and configs[4]: (a) the 500 American+dividend options of config 2 priced ONCE, sharded over
-    all ranks (strong scaling: the "500 options in <= 2 ms on 8 GPUs" target), and (b) a 10 000-option European
-    chain (101x51, N=50) sharded the same way.  Items are block-partitioned by cost (hadi_partition); every rank
-    solves its slice and the values are all-gathered (NCCL) — wall time from the barrier before the launches to
-    the gathered values on the host, max over ranks, best of 5."""
+    """Strong scaling, one workload split over all ranks (items block-partitioned by cost, hadi_partition; every
+    rank solves its slice; values all-gathered): (a) the 500 American+dividend options of config 2 (the "500
+    options in <= 2 ms on 8 GPUs" target), (b) the SURVEY C5 chain (10 000 European options, mixed maturities),
+    (c) the finite-difference Jacobian of the C3 surface (100 points x 6 solves, 101x51).  Wall time from the barrier
+    before the launches to the gathered values on the host, max over ranks, best of 5; `digest` is a sha256 prefix of
+    the gathered values — it must not change with the number of ranks."""
     import importlib.util
     import numpy as np
     import __graft_entry__ as ge
@@ -214,15 +291,17 @@ def sharded_chains(hadi, ctx, torch, dev, rank, world, dist):
     spec.loader.exec_module(hd)
     mdl = hadi.make_model(**BASE)
     out = {}
+    K5, T5, N5 = c5_chain()
+    K3, T3, N3 = c3_surface()
     cases = (("config2_500_sharded", hadi.make_numerics(M1, M2, THETA, hadi.AMERICAN, hadi.CALL, hadi.DOUGLAS, DIVS),
-              [70.0 + 0.12 * i for i in range(NOPT)]),
-             ("chain_10k_sharded", hadi.make_numerics(M1, M2, THETA), [60.0 + 0.008 * i for i in range(10000)]))
-    for name, num, strikes in cases:
-        pts, n = hadi.make_points(strikes, 1.0, NSTEP)
-        costs = hadi.item_costs(num, pts, n, hadi.MODE_PRICE)
+              hadi.make_points([70.0 + 0.12 * i for i in range(NOPT)], 1.0, NSTEP), hadi.MODE_PRICE),
+             ("c5_chain_10k_sharded", hadi.make_numerics(M1, M2, THETA), hadi.make_points(K5, T5, N5), hadi.MODE_PRICE),
+             ("c3_jacobian_600_sharded", hadi.make_numerics(M1, M2, THETA), hadi.make_points(K3, T3, N3), hadi.MODE_JACOBIAN))
+    for name, num, (pts, n), mode in cases:
+        costs = hadi.item_costs(num, pts, n, mode)
         sl = hd.slices(hadi, costs, world)
         b, e = sl[rank]
-        bt = ctx.batch(mdl, num, pts, n, begin=b, end=e) if e > b else None
+        bt = ctx.batch(mdl, num, pts, n, mode=mode, begin=b, end=e) if e > b else None
         counts = [x[1] - x[0] for x in sl]
         best = None
         for rep in range(7):
@@ -241,10 +320,111 @@ def sharded_chains(hadi, ctx, torch, dev, rank, world, dist):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             if rep >= 2:
                 best = float(t[0]) if best is None else min(best, float(t[0]))
-        out[name] = {"options": len(strikes), "wall_ms": round(best, 3), "solves_per_s": round(len(strikes) / (best * 1e-3), 1),
-                     "checksum": float(np.sum(vals))}
+        out[name] = {"items": int(len(costs)), "wall_ms": round(best, 3),
+                     "solves_per_s": round(len(costs) / (best * 1e-3), 1),
+                     "checksum": float(np.sum(vals)), "digest": _digest(vals)}
         if bt is not None:
             bt.destroy()
+        if world > 1:
+            # the same workload on ONE GPU in the same run (rank 0, the others wait): strong-scaling efficiency
+            one = None
+            if rank == 0:
+                b1 = ctx.batch(mdl, num, pts, n, mode=mode)
+                for rep in range(5):
+                    torch.cuda.synchronize(dev)
+                    t0 = time.perf_counter()
+                    b1.launch()
+                    v1 = b1.fetch()
+                    ms = (time.perf_counter() - t0) * 1e3
+                    if rep >= 2:
+                        one = ms if one is None else min(one, ms)
+                b1.destroy()
+                out[name]["single_gpu_ms"] = round(one, 3)
+                out[name]["strong_scaling_efficiency"] = round(one / (world * best), 4)
+                out[name]["equals_single_gpu"] = bool(np.array_equal(v1, vals))
+            dist.barrier()
+    return out
+
+
+def c5_cpu_baseline():
+    """The reference's own code on the host cores on a bounded sample of the C5 chain (every 50th option:
+    200 options covering all four maturities; compute_base_prices_multi_maturity timed alone)."""
+    import numpy as np
+
+    ref = ref_lib()
+    if ref is None:
+        return None
+    R, cores = ref
+    K, T, N = c5_chain()
+    idx = list(range(0, 10000, 50))
+    Ks, Ts = np.array([K[i] for i in idx]), np.array([T[i] for i in idx])
+    Ns = np.array([N[i] for i in idx], dtype=np.int32)
+    R.solve_batch(Ks[:cores], Ns[:cores], Ts[:cores] / Ns[:cores], maturities=Ts[:cores], m1=M1, m2=M2, theta=THETA, multi=1, **BASE)
+    p = R.solve_batch(Ks, Ns, Ts / Ns, maturities=Ts, m1=M1, m2=M2, theta=THETA, multi=1, **BASE)["prices"]
+    dt = R.last_compute_seconds()
+    return {"value": len(idx) / dt, "unit": "solves/s", "cores": cores, "kind": "reference",
+            "sample": "every 50th option of the chain (200 options), %.2f s in the reference entry point" % dt}, p, idx
+
+
+def config4_block(hadi, ctx, peaks, with_cpu):
+    """BASELINE configs[3]: European Craig-Sneyd on the 401x201 grid, N = 200 — beyond shared memory, so U, Y and
+    the Craig-Sneyd stage arrays live in L2-resident global scratch (one CTA per solve; a thread-block cluster per
+    solve when there are few).  Memory-bound by construction: roofline = algorithmic bytes (9 arrays x 8 B x P per
+    step) over the kernel time, against the measured HBM copy bandwidth."""
+    m1, m2, N = 400, 200, 200
+    Pl = (m1 + 1) * (m2 + 1)
+    mdl = hadi.make_model(**BASE)
+    num = hadi.make_numerics(m1, m2, THETA, hadi.EUROPEAN, hadi.CALL, hadi.CRAIG_SNEYD, None)
+    out = {"workload": "config4: European call, Craig-Sneyd, 401x201 grid, N=200, strikes 100+0.1k"}
+    hbm = peaks.get("hbm_gbs") or 6552.3
+    for nopt in (1, 8, 148):
+        pts, n = hadi.make_points([100.0 + 0.1 * k for k in range(nopt)], 1.0, N)
+        bt = ctx.batch(mdl, num, pts, n)
+        ts = []
+        for r in range(3 if nopt < 148 else 2):
+            bt.launch()
+            v = bt.fetch()
+            ts.append(bt.elapsed_ms())
+        ms = min(ts)
+        byts = nopt * N * Pl * 8 * 9
+        out["n%d" % nopt] = {"solves": nopt, "ms": round(ms, 3), "ms_per_solve": round(ms / nopt, 3),
+                             "solves_per_s": round(nopt / (ms * 1e-3), 2),
+                             "roofline": {"bound": "hbm", "achieved": round(byts / ms / 1e6, 1), "peak": hbm,
+                                          "unit": "GB/s", "frac": round(byts / ms / 1e6 / hbm, 4)},
+                             "price0": repr(float(v[0]))}
+        bt.destroy()
+    out["golden_price_K100"] = "8.8920027296371611"
+    if with_cpu:
+        ref = ref_lib()
+        if ref is not None:
+            R = ref[0]
+            t0 = time.perf_counter()
+            pr = R.host_scheme(1, K=100.0, T=1.0, m1=m1, m2=m2, N=N, theta=THETA, **BASE)
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": 1.0 / dt, "unit": "solves/s", "cores": 1, "kind": "reference",
+                                   "sample": "1 solve through the reference's CS_scheme_shuffled (host matrix classes, serial), %.2f s" % dt,
+                                   "price": repr(float(pr)), "parity": repr(float(pr)) == out["n1"]["price0"]}
+    return out
+
+
+def instance_sweep(hadi, ctx):
+    """The reference's own benchmark protocol (src/perfomance_test.cpp:46-57): European calls, strike 85, 51x26 grid,
+    N = 20, instance counts {1, 10, 20, 50, 100, 200, 300, 500}, mean of 10 runs — end to end through
+    hadi_price_batch with host buffers (the latency regime of small batches)."""
+    mdl = hadi.make_model(**BASE)
+    num = hadi.make_numerics(50, 25, THETA)
+    out = {}
+    for ninst in (1, 10, 20, 50, 100, 200, 300, 500):
+        pts, n = hadi.make_points([85.0] * ninst, 1.0, 20)
+        for _ in range(3):
+            ctx.price_batch(mdl, num, pts, n)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            r = ctx.price_batch(mdl, num, pts, n)
+        ms = (time.perf_counter() - t0) * 1e3 / 10
+        out[str(ninst)] = {"ms": round(ms, 4), "ms_per_instance": round(ms / ninst, 5),
+                           "solves_per_s": round(ninst / (ms * 1e-3), 1)}
+    out["price_K85"] = repr(float(r["prices"][0]))
     return out
 
 
@@ -255,6 +435,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="headline + LM + sharded only (no config 4, no instance sweep)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -345,24 +526,31 @@ def main():
         hd = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(hd)
         comm = hd.make_comm(hadi, rank, world, device=dev, dist=dist)
-    lm = lm_calibration(hadi, ctx, comm)
+    lm = lm_calibration(hadi, ctx, comm, world, rank, dist)
     sharded = sharded_chains(hadi, ctx, torch, dev, rank, world, dist)
     if dist is not None:
         dist.barrier()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    config4 = sweep = None
+    if rank == 0 and world == 1 and not args.quick:
+        config4 = config4_block(hadi, ctx, peaks, with_cpu=not args.no_cpu_baseline)
+        sweep = instance_sweep(hadi, ctx)
 
     if rank == 0:
         unfused, fma, dep_ns = hadi.measure_fp64(local_rank)
         ms_kernel = total_ms / args.steps
         flops = NOPT * NSTEP * P * FLOPS_PER_POINT_STEP
         achieved = flops / (ms_kernel * 1e-3) / 1e12
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
         traffic = None
-        try:   # DRAM bytes of one launch of this kernel from the committed ncu --set full capture
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["dram_bytes_per_launch"]
+        try:   # DRAM bytes of one launch of this kernel from the latest committed ncu --set full capture
+            import glob
+
+            latest = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))[-1]
+            traffic = json.load(open(latest))["dram_bytes_per_launch"]
         except Exception:
             pass
         roofline = {"bound": "fp64", "achieved": achieved, "peak": unfused, "unit": "TFLOP/s",
@@ -377,9 +565,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "options_per_gpu": NOPT, "grid": "101x51", "time_steps": NSTEP,
-                           "l2": "256 MiB buffer written between timed iterations (L2 flush)",
-                           "timing": "CUDA events around each launch on the launching stream, summed over the steps, max over ranks"},
+                "config": bench_config(),
                 "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": (h1 - h0) // args.steps,
                         "d2h_bytes_per_step": (d1 - d0) // args.steps, "ms_per_step": e2e_ms_max / args.steps,
                         "api": "hadi_price_batch (C ABI, host buffers)"},
@@ -388,6 +574,8 @@ def main():
                 "clocks": clocks,
                 "lm": lm,
                 "sharded": sharded,
+                "config4": config4,
+                "instance_sweep_51x26x20": sweep,
                 "grid_point_steps_per_s": value * NSTEP * P}
         if world == 1 and not args.no_cpu_baseline:
             base, ref_prices, ref_strikes = cpu_baseline()
@@ -395,6 +583,15 @@ def main():
             import numpy as np
 
             line["cpu_baseline"]["parity_on_sample"] = bool(np.array_equal(np.asarray(ref_prices), np.asarray(out["prices"][:len(ref_strikes)])))
+            c5 = c5_cpu_baseline()
+            if c5 is not None:
+                # parity of the sample against the GPU chain, and the CPU rate beside the sharded GPU rate
+                K5, T5, N5 = c5_chain()
+                idx = c5[2]
+                pts5, n5 = hadi.make_points([K5[i] for i in idx], [T5[i] for i in idx], [N5[i] for i in idx])
+                g5 = ctx.price_batch(mdl, hadi.make_numerics(M1, M2, THETA), pts5, n5)["prices"]
+                c5[0]["parity_on_sample"] = bool(np.array_equal(np.asarray(c5[1]), np.asarray(g5)))
+                line["sharded"]["c5_chain_10k_sharded"]["cpu_baseline"] = c5[0]
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -114,6 +114,7 @@ typedef struct {
   int converged;
   int pde_solves;
   double gpu_ms;     /* device time of all solver launches (CUDA events) */
+  long long exact_reruns;  /* solves repeated with IEEE divisions (see hadi_exact_reruns); 0 on option data so far */
 } hadi_lm_result;
 
 /* ---- context ------------------------------------------------------------------------------- */
@@ -123,11 +124,18 @@ const char* hadi_last_error(const hadi_ctx* ctx);
 const char* hadi_version(void);
 /* number of hadi kernels launched by this context so far (bench.py's gpu_launches) */
 long long hadi_kernel_launches(const hadi_ctx* ctx);
+/* Solves this context had to repeat with IEEE divisions because a guarded fast division left its operand range
+ *  or a split-schedule hand-off timed out.  The published values are exact either way; a
+ * non-zero count means those solves cost twice the time.  Updated by every hadi_batch_fetch / one-call entry point. */
+long long hadi_exact_reruns(const hadi_ctx* ctx);
+/* the same for the last fetched launch of one batch */
+long long hadi_batch_exact_reruns(const hadi_batch* b);
 /* cumulative host->device / device->host bytes moved by this context */
 int hadi_transfer_bytes(const hadi_ctx* ctx, long long* h2d, long long* d2h);
 
 /* ---- one-call entry points (host buffers in, host buffers out; synchronous) ------------------- */
-/* prices[n]; U_out[n*(m1+1)*(m2+1)] and lambda_out (same shape) may be NULL. */
+/* prices[n] are written at points[k].global_index (as the reference's multi-maturity drivers do); the optional
+ * U_out[n*(m1+1)*(m2+1)] and lambda_out (same shape; may be NULL) are in INPUT order: block k belongs to points[k]. */
 int hadi_price_batch(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
                      const hadi_point* points, double* prices, double* U_out, double* lambda_out);
 /* J[n*5] row-major, base_prices[n]. */
@@ -220,8 +228,29 @@ typedef struct {
   void* user;
 } hadi_comm;
 
+/* In-library exchange: an NCCL communicator owned by the context (one context = one device = one rank).  Rank 0
+ * obtains an id with hadi_nccl_unique_id and hands the 128 bytes to every rank by any means (MPI, a file,
+ * torch.distributed); every rank then calls hadi_comm_init.  With a communicator attached, hadi_calibrate /
+ * hadi_calibrate_ex (comm == NULL) and the *_sharded entry points split the work items over the ranks
+ * (hadi_partition), each rank's kernel publishes its values straight into its slot of a device gather buffer, and one
+ * ncclAllGather on the context's stream plus one device-to-host copy per solver call return every value to every
+ * rank — no host hop, no callback.  NCCL is loaded with dlopen("libnccl.so.2") on first use (HADI_NCCL_LIB overrides
+ * the name); libhadi.so itself does not link it. */
+#define HADI_NCCL_ID_BYTES 128
+int hadi_nccl_unique_id(void* id128);
+int hadi_comm_init(hadi_ctx* ctx, int world, int rank, const void* id128);
+void hadi_comm_finalize(hadi_ctx* ctx);
+int hadi_comm_world(const hadi_ctx* ctx);
+int hadi_comm_rank(const hadi_ctx* ctx);
+/* SPMD one-call entry points: every rank passes the same arguments and receives every result */
+int hadi_price_batch_sharded(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
+                             const hadi_point* points, double* prices);
+int hadi_jacobian_batch_sharded(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
+                                const hadi_point* points, const hadi_jacobian_options* opt, double* J,
+                                double* base_prices);
+
 /* Full LM calibration (host loop of src/heston_calibration.cpp:2692-2831 around the batched
- * solver).  comm may be NULL (single GPU). */
+ * solver).  comm may be NULL: single GPU, or the context's own communicator when one is attached (hadi_comm_init). */
 int hadi_calibrate(hadi_ctx* ctx, const hadi_model* initial, const hadi_numerics* num, int n,
                    const hadi_point* points, const double* market_prices, const hadi_lm_options* opt,
                    const hadi_comm* comm, hadi_lm_result* result);

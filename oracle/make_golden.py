@@ -60,9 +60,136 @@ def market_fixtures(R):
     json.dump(dict(divs=DIVS, market=cases, implied_vol=iv), open(os.path.join(OUT, "market.json"), "w"), indent=0)
 
 
+def lm_trajectory(R, K, T, N, market, *, m1, m2, style, divs, multi, max_iter, tol, dtol, init):
+    """The reference's LM loop (src/heston_calibration.cpp:204-417 single maturity, :2692-2831 multi-maturity,
+    :3568-3716 American + dividends) driven through the reference's own compute_jacobian* /
+    compute_base_prices* / compute_parameter_update_on_device.  Returns the trajectory and the final state the
+    drivers print (params, final_error, iteration_count, lambda)."""
+    K, T = np.asarray(K, dtype=np.float64), np.asarray(T, dtype=np.float64)
+    N = np.asarray(N, dtype=np.int32)
+    dt = T / N
+    cur = dict(init)
+    lam = 0.01
+    traj = []
+    final_error, iters, converged, solves = 100.0, 0, 0, 0
+    kw = dict(m1=m1, m2=m2, style=style, divs=divs, multi=multi)
+    if multi:
+        kw["maturities"] = T
+    for it in range(max_iter):
+        r = R.solve_batch(K, N, dt, jac=1, **kw, **cur)
+        solves += 6 * K.size
+        res = market - r["prices"]
+        delta = R.lm_update(r["J"], res, lam)
+        nw = dict(cur)
+        nw["kappa"] = max(1e-3, cur["kappa"] + delta[0])
+        nw["eta"] = max(1e-2, cur["eta"] + delta[1])
+        nw["sigma"] = max(1e-2, cur["sigma"] + delta[2])
+        nw["rho"] = min(1.0, max(-1.0, cur["rho"] + delta[3]))
+        nw["V0"] = max(1e-2, cur["V0"] + delta[4])
+        dn = 0.0
+        for d in delta:
+            dn += d * d
+        dn = math.sqrt(dn)
+        err = 0.0
+        for x in res:
+            err += x * x
+        step = dict(iter=it, lam=lam, err=repr(float(err)), delta_norm=repr(float(dn)),
+                    delta=[repr(float(x)) for x in delta],
+                    clamped=[k for k in ("kappa", "eta", "sigma", "rho", "V0")
+                             if nw[k] != cur[k] + delta[("kappa", "eta", "sigma", "rho", "V0").index(k)]])
+        if dn < dtol or err < tol:
+            cur = nw
+            final_error, iters, converged = err, it + 1, 1
+            traj.append(step)
+            break
+        r2 = R.solve_batch(K, N, dt, **kw, **nw)
+        solves += K.size
+        nerr = 0.0
+        for x in market - r2["prices"]:
+            nerr += x * x
+        step["new_err"] = repr(float(nerr))
+        step["accepted"] = bool(nerr < err)
+        if nerr < err:
+            cur = nw
+            lam = max(lam / 10.0, 1e-7)
+        else:
+            lam = min(lam * 10.0, 1e7)
+        final_error, iters = min(nerr, err), it + 1
+        traj.append(step)
+    return dict(n=int(K.size), tol=tol, delta_tol=dtol, max_iter=max_iter, iterations=iters, converged=converged,
+                pde_solves=solves, final_error=repr(float(final_error)), lam=repr(float(lam)), trajectory=traj,
+                params=[repr(float(cur[k])) for k in ("kappa", "eta", "sigma", "rho", "V0")])
+
+
+def more_fixtures():
+    """Round-2 fixtures (python oracle/make_golden.py more): Jacobians of all four entry-point families on the
+    101x51 grid, the LM calibration of BASELINE config 3 (10 strikes x 10 maturities) on both grids, and the
+    trajectories of the reference's two other shipped LM drivers (test_calibration_european,
+    src/heston_calibration.cpp:26; test_calibration_american_divident_multi_maturity, :3245).  Computed with the
+    OpenMP flavour of oracle/_ref (each thread owns its option instance: bit-identical to the serial build)."""
+    R = RefLib(omp=True)
+    R.set_threads(os.cpu_count() or 1)
+    init = {k: BASE[k] for k in ("S0", "V0", "r_d", "r_f", "rho", "sigma", "kappa", "eta", "theta")}
+    # ---- Jacobians at 101x51 (N = 20), three strikes per family
+    jac = []
+    for (style, dv) in [(0, None), (1, None), (0, DIVS), (1, DIVS)]:
+        strikes = [92.0, 100.0, 111.0]
+        r = R.solve_batch(strikes, 20, 1.0 / 20, m1=100, m2=50, style=style, divs=dv, jac=1, eps=1e-6, **BASE)
+        jac.append(dict(m1=100, m2=50, N=20, style=style, div=dv is not None, strikes=strikes, eps=1e-6,
+                        base=[repr(float(x)) for x in r["prices"]],
+                        J=[[repr(float(x)) for x in row] for row in r["J"]]))
+    json.dump(dict(base=BASE, divs=DIVS, cases=jac), open(os.path.join(OUT, "jacobians_101x51.json"), "w"), indent=0)
+    out = {}
+    # ---- BASELINE config 3 (SURVEY C3): strikes 95 + s, maturities of src/heston_calibration.cpp:2485-2489
+    mats = [1.0 + i * 0.25 if i < 8 else 3.0 + (i - 8) * 0.5 for i in range(10)]
+    K, T, N = [], [], []
+    for Tm in mats:
+        for s in range(10):
+            K.append(95.0 + 1.0 * s)
+            T.append(Tm)
+            N.append(max(20, int(Tm * 20)))
+    market = np.array([R.bs_call(100.0, k, 0.025, 0.2, t) for k, t in zip(K, T)])
+    n = len(K)
+    for name, (m1, m2) in (("config3_51x26", (50, 25)), ("config3_101x51", (100, 50))):
+        out[name] = lm_trajectory(R, K, T, N, market, m1=m1, m2=m2, style=0, divs=None, multi=1, max_iter=15,
+                                  tol=0.1 * math.sqrt(n), dtol=0.1 * (1.0 + math.log(n)), init=init)
+        out[name].update(m1=m1, m2=m2, style=0)
+    # ---- test_calibration_european: 60 strikes 70..129, T = 1, N = 20, 51x26, tol = delta_tol = 0.1
+    K = [100.0 * 0.7 + i * 1 for i in range(60)]
+    market = np.array([R.bs_call(100.0, k, 0.025, 0.2, 1.0) for k in K])
+    out["shipped_european"] = lm_trajectory(R, K, [1.0] * 60, [20] * 60, market, m1=50, m2=25, style=0, divs=None,
+                                            multi=0, max_iter=15, tol=0.1, dtol=0.1, init=init)
+    out["shipped_european"].update(m1=50, m2=25, style=0,
+                                   survey="4 iterations, kappa=47.9119 eta=0.0312648 sigma=0.01 rho=-1 v0=0.0946873 err=0.0836893")
+    # ---- test_calibration_american_divident_multi_maturity: 3 maturities x 60 strikes, market from the model
+    divs = ([0.2, 0.4, 0.6, 0.8], [0.10] * 4, [0.0005] * 4)
+    K, T, N = [], [], []
+    for Tm in (1.0, 1.5, 2.0):
+        for i in range(60):
+            K.append(100.0 * 0.7 + i * 1)
+            T.append(Tm)
+            N.append(max(20, int(Tm * 20)))
+    Na = np.asarray(N, dtype=np.int32)
+    Ta = np.asarray(T)
+    gen = dict(init, kappa=3.0, eta=0.1, sigma=0.05, rho=0.2, V0=0.06)
+    market = R.solve_batch(K, Na, Ta / Na, maturities=Ta, m1=50, m2=25, style=1, divs=divs, multi=1, **gen)["prices"].copy()
+    out["shipped_american_dividend"] = lm_trajectory(R, K, T, N, market, m1=50, m2=25, style=1, divs=divs, multi=1,
+                                                     max_iter=20, tol=0.1, dtol=0.3 * 0.1, init=init)
+    out["shipped_american_dividend"].update(
+        m1=50, m2=25, style=1, divs=divs, market_params=[3.0, 0.1, 0.05, 0.2, 0.06],
+        market_sha256=digest(market),
+        survey="18 iterations, kappa=0.52875 eta=0.114716 sigma=0.0901574 rho=0.120892 v0=0.0800021 err=0.19322")
+    json.dump(out, open(os.path.join(OUT, "lm_more.json"), "w"), indent=0)
+    for k, v in out.items():
+        print(k, v["iterations"], v["converged"], v["params"], v["final_error"], v["pde_solves"])
+
+
 def main():
     R = RefLib()
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "more":
+        more_fixtures()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "market":
         market_fixtures(R)
         return

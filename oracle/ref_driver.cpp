@@ -17,7 +17,11 @@
 // src/heston_calibration.cpp:2563-2660; it contains no solver arithmetic.
 #include <Kokkos_Core.hpp>
 
+#include <chrono>
 #include <cstdio>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <iostream>
 #include <sstream>
 #include <cstring>
@@ -161,7 +165,34 @@ void build_problem(Problem& p, int n, const double* strikes, const double* matur
 
 }  // namespace
 
+namespace {
+double g_last_compute_s = 0.0;   // wall time of the reference entry point alone in the last hadi_ref_solve_batch
+}
+
 extern "C" {
+
+// Seconds the reference's own entry point (compute_base_prices* / compute_jacobian*) took in the last
+// hadi_ref_solve_batch call: the problem set-up of this driver (grids, U_0, workspace) is outside it.
+double hadi_ref_last_compute_seconds() { return g_last_compute_s; }
+// Host threads the league loop of the Kokkos stand-in spreads over (1 in the serial build).
+int hadi_ref_threads() {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+// Overrides OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1 to its children); returns the count in effect.
+int hadi_ref_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
+  return 1;
+#endif
+}
 
 // Reference grid (src/grid.cpp:16-96).  Outputs: s[m1+1], ds[m1], v[m2+1], dv[m2].
 int hadi_ref_grid(int m1, double S, double S_0, double K, double c, int m2, double V, double V_0,
@@ -208,6 +239,7 @@ int hadi_ref_solve_batch(int n, const double* strikes, const double* maturities,
   }
   Kokkos::TeamPolicy<Device> policy(n, Kokkos::AUTO);
   const bool div = nd > 0;
+  const auto t_compute0 = std::chrono::steady_clock::now();
   if (multi) {
     if (style == 0 && !div) {
       if (jac)
@@ -265,6 +297,7 @@ int hadi_ref_solve_batch(int n, const double* strikes, const double* maturities,
                                              P, N, theta, dt, n, p.A0, p.A1, p.A2, p.bounds,
                                              p.deviceGrids, p.U_0, *p.ws, nd, dd, da, dp, base);
   }
+  g_last_compute_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_compute0).count();
   for (int i = 0; i < n; ++i) out_prices[i] = base(i);
   if (jac && out_J)
     for (int i = 0; i < n; ++i)

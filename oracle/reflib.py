@@ -53,6 +53,19 @@ class RefLib:
         L.hadi_ref_dump_operators.argtypes = ([C.c_double, C.c_int] + [C.c_double] * 9 +
                                               [C.c_int, C.c_int, C.c_double] + [_dp] * 8)
         L.hadi_ref_run_shipped.argtypes = [C.c_int]
+        L.hadi_ref_last_compute_seconds.restype = C.c_double
+        L.hadi_ref_set_threads.argtypes = [C.c_int]
+
+    def set_threads(self, n):
+        """Host threads of the league loop (overrides OMP_NUM_THREADS); returns the count in effect."""
+        return int(self.lib.hadi_ref_set_threads(int(n)))
+
+    def threads(self):
+        return int(self.lib.hadi_ref_threads())
+
+    def last_compute_seconds(self):
+        """Wall time of the reference entry point alone in the last solve_batch (driver set-up excluded)."""
+        return float(self.lib.hadi_ref_last_compute_seconds())
 
     def grid(self, m1, m2, K, S0, V0, S=None, c=None, V=5.0, d=5.0 / 500):
         S = 8 * K if S is None else S

@@ -10,6 +10,8 @@
 // CPU) uses the same libm, and bit-equal grids are a precondition for bit-equal prices.
 // There is no CPU solver in this file: every PDE solve goes through the CUDA kernel.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types and prototypes only: the library is loaded with dlopen when a communicator is attached
 
 #include <algorithm>
 #include <chrono>
@@ -58,6 +60,13 @@ struct hadi_ctx {
   size_t spool_cap = 0, spool_used = 0;   // doubles
   bool spool_tried = false;
   std::map<std::tuple<int, uint64_t, uint64_t>, DevGrid> s_dev;
+  // In-library exchange (multi-GPU): an NCCL communicator bound to this context's device; all-gathers run on
+  // `stream` behind the kernel whose epilogue wrote this rank's values straight into the gather buffer.
+  ncclComm_t nccl = nullptr;
+  int nccl_world = 1, nccl_rank = 0;
+  double* d_gather = nullptr;   // [world][gather_cap] doubles
+  double* h_gather = nullptr;   // pinned mirror
+  size_t gather_cap = 0;        // doubles per rank
   // kernel plans per (m1, m2, scheme, few items, forced variant): the occupancy queries cost tens of microseconds
   std::map<std::tuple<int, int, int, int, std::string>, std::pair<int, HadiPlan>> plans;
 };
@@ -72,7 +81,8 @@ struct hadi_batch {
   HadiPlan plan{};
   int grid_ctas = 0;
   std::vector<int> bufs;  // indices into ctx->pool owned by this batch
-  double* h_values = nullptr;  // pinned
+  double* h_values = nullptr;  // pinned; one extra word past the values carries the re-solve counter
+  long long reruns = 0;        // items of the last fetched launch that were re-solved with IEEE divisions
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool launched = false;
 };
@@ -85,6 +95,43 @@ int fail(hadi_ctx* ctx, int code, const std::string& msg) {
 }
 int cuda_fail(hadi_ctx* ctx, cudaError_t e, const char* what) {
   return fail(ctx, HADI_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+// ---- NCCL, loaded on demand ---------------------------------------------------------------------
+// libhadi.so does not link NCCL: a single-GPU user never needs it, and in a PyTorch process the library torch
+// already loaded (same soname) is the one dlopen returns, so both sides share one NCCL.
+struct NcclApi {
+  void* lib = nullptr;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  bool ok() const { return lib && GetUniqueId && CommInitRank && CommDestroy && AllGather && GetErrorString; }
+};
+NcclApi& nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* names[] = {getenv("HADI_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+      if (!nm || !*nm) continue;
+      api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (api.lib) break;
+    }
+    if (api.lib) {
+      api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
+      api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
+      api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
+      api.AllGather = (decltype(api.AllGather))dlsym(api.lib, "ncclAllGather");
+      api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
+    }
+  }
+  return api;
+}
+int nccl_fail(hadi_ctx* ctx, ncclResult_t r, const char* what) {
+  return fail(ctx, HADI_ERR_COMM, std::string(what) + ": " + (nccl_api().ok() ? nccl_api().GetErrorString(r) : "NCCL not loaded"));
 }
 
 uint64_t bits(double x) {
@@ -342,9 +389,53 @@ void hadi_destroy(hadi_ctx* ctx) {
       cudaFree(b.p);
   }
   if (ctx->d_spool) cudaFree(ctx->d_spool);
+  if (ctx->nccl && nccl_api().ok()) nccl_api().CommDestroy(ctx->nccl);
+  if (ctx->d_gather) cudaFree(ctx->d_gather);
+  if (ctx->h_gather) cudaFreeHost(ctx->h_gather);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
+
+// ---- in-library multi-GPU exchange -------------------------------------------------
+int hadi_nccl_unique_id(void* id128) {
+  if (!id128) return HADI_ERR_ARG;
+  if (!nccl_api().ok()) return HADI_ERR_COMM;
+  ncclUniqueId id;
+  if (nccl_api().GetUniqueId(&id) != ncclSuccess) return HADI_ERR_COMM;
+  static_assert(sizeof(id) == HADI_NCCL_ID_BYTES, "ncclUniqueId is 128 bytes");
+  std::memcpy(id128, &id, sizeof id);
+  return HADI_OK;
+}
+
+int hadi_comm_init(hadi_ctx* ctx, int world, int rank, const void* id128) {
+  if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) return HADI_ERR_ARG;
+  if (ctx->nccl) return fail(ctx, HADI_ERR_ARG, "a communicator is already attached");
+  if (!nccl_api().ok()) return fail(ctx, HADI_ERR_COMM, "libnccl.so.2 could not be loaded (set HADI_NCCL_LIB)");
+  cudaSetDevice(ctx->device);
+  ncclUniqueId id;
+  std::memcpy(&id, id128, sizeof id);
+  const ncclResult_t r = nccl_api().CommInitRank(&ctx->nccl, world, id, rank);
+  if (r != ncclSuccess) {
+    ctx->nccl = nullptr;
+    return nccl_fail(ctx, r, "ncclCommInitRank");
+  }
+  ctx->nccl_world = world;
+  ctx->nccl_rank = rank;
+  return HADI_OK;
+}
+
+void hadi_comm_finalize(hadi_ctx* ctx) {
+  if (!ctx || !ctx->nccl) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (nccl_api().ok()) nccl_api().CommDestroy(ctx->nccl);
+  ctx->nccl = nullptr;
+  ctx->nccl_world = 1;
+  ctx->nccl_rank = 0;
+}
+
+int hadi_comm_world(const hadi_ctx* ctx) { return ctx ? ctx->nccl_world : 0; }
+int hadi_comm_rank(const hadi_ctx* ctx) { return ctx ? ctx->nccl_rank : -1; }
 
 const char* hadi_last_error(const hadi_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
 long long hadi_kernel_launches(const hadi_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -523,7 +614,8 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
   const int n_it_plan = (item_end < 0 ? n * n_columns(mode) : item_end) - item_begin;
   const auto plan_key = std::make_tuple(num->m1, num->m2, num->scheme,
                                         (int)(n_it_plan * HADI_CLUSTER <= 148 && num->num_dividends == 0),
-                                        std::string(forced_variant ? forced_variant : ""));
+                                        std::string(forced_variant ? forced_variant : "") + "|" +
+                                            std::string(getenv("HADI_NO_DUO") ? getenv("HADI_NO_DUO") : ""));
   const auto plan_hit = ctx->plans.find(plan_key);
   if (plan_hit != ctx->plans.end() && plan_hit->second.first == 0) {
     plan = plan_hit->second.second;
@@ -690,7 +782,7 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
     const char* ns = getenv("HADI_NO_SPLIT");
     const char* su = getenv("HADI_SPLIT_SETUP");
     const double setup = su ? atof(su) : 1.5;
-    if (!(ns && atoi(ns) != 0) && !plan.global_state && plan.cluster <= 1 && plan.variant <= 3 && !getenv("HADI_MAX_CTAS"))
+    if (!(ns && atoi(ns) != 0) && !plan.global_state && plan.cluster <= 1 && (plan.variant <= 3 || plan.variant == 8) && !getenv("HADI_MAX_CTAS"))
       use_split = build_split_schedule(items, slots, setup, &sched);
   }
 
@@ -715,8 +807,8 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
   };
   char* h_stage = (char*)take(staging, true);
   char* d_stage = (char*)take(staging, false);
-  b->h_values = (double*)take(sizeof(double) * (size_t)std::max(n_items, 1) * b->stride, true);
-  double* d_values = (double*)take(sizeof(double) * (size_t)std::max(n_items, 1) * b->stride, false);
+  b->h_values = (double*)take(sizeof(double) * ((size_t)std::max(n_items, 1) * b->stride + 1), true);
+  double* d_values = (double*)take(sizeof(double) * ((size_t)std::max(n_items, 1) * b->stride + 1), false);
   int* d_counter = (int*)take(256, false);
 
   b->plan = plan;
@@ -787,6 +879,7 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
   L.counter = d_counter;
   L.out_values = d_values;
   L.out_stride = b->stride;
+  L.reruns = reinterpret_cast<unsigned long long*>(d_values + (size_t)std::max(n_items, 1) * b->stride);
   L.out_U = nullptr;
   L.out_lam = nullptr;
   L.scheme = num->scheme;
@@ -795,6 +888,7 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
     int* hs = (int*)take(sizeof(int) * (size_t)sched.n_hand, false);
     double* hd = (double*)take(sizeof(double) * 2 * (size_t)P * (size_t)sched.n_hand, false);
     if (!hs || !hd) {
+      cudaStreamSynchronize(ctx->stream);   // the staging copies above are in flight: do not hand their buffers back yet
       release_all();
       return HADI_ERR_NOMEM;
     }
@@ -805,10 +899,15 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
     b->n_hand = sched.n_hand;
   }
   L.dbg_step = L.dbg_phase = 0;
+  L.flags = HADI_FLAGS_DEFAULT;
+  if (const char* fl = getenv("HADI_FLAGS")) L.flags = atoi(fl);
   if (const char* ds = getenv("HADI_DEBUG_STOP")) sscanf(ds, "%d:%d", &L.dbg_step, &L.dbg_phase);
   L.prof = (long long*)take(sizeof(long long) * (8 * (size_t)b->grid_ctas + 1), false);
   if (L.prof) cudaMemsetAsync(L.prof, 0, sizeof(long long) * (8 * (size_t)b->grid_ctas + 1), ctx->stream);
   if (cudaEventCreate(&b->ev0) != cudaSuccess || cudaEventCreate(&b->ev1) != cudaSuccess) {
+    cudaStreamSynchronize(ctx->stream);
+    if (b->ev0) cudaEventDestroy(b->ev0);
+    b->ev0 = nullptr;
     release_all();
     return cuda_fail(ctx, cudaGetLastError(), "event");
   }
@@ -817,6 +916,7 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
 }
 
 int hadi_batch_num_items(const hadi_batch* b) { return b ? b->n_items : 0; }
+long long hadi_batch_exact_reruns(const hadi_batch* b) { return b ? b->reruns : 0; }
 int hadi_batch_values_per_item(const hadi_batch* b) { return b ? b->stride : 0; }
 double* hadi_batch_values_dev(hadi_batch* b) { return b ? b->L.out_values : nullptr; }
 
@@ -825,6 +925,7 @@ int hadi_batch_launch(hadi_batch* b) {
   hadi_ctx* ctx = b->ctx;
   cudaSetDevice(ctx->device);
   cudaError_t e = cudaMemsetAsync(b->L.counter, 0, sizeof(int), ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(b->L.reruns, 0, sizeof(unsigned long long), ctx->stream);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "memset");
   if (b->n_hand > 0) {
     e = cudaMemsetAsync(b->L.hand_state, 0, sizeof(int) * (size_t)b->n_hand, ctx->stream);
@@ -846,13 +947,18 @@ int hadi_batch_fetch(hadi_batch* b, double* values) {
   hadi_ctx* ctx = b->ctx;
   cudaSetDevice(ctx->device);
   const size_t nv = (size_t)b->n_items * (size_t)b->stride;
-  cudaError_t e = cudaMemcpyAsync(b->h_values, b->L.out_values, sizeof(double) * std::max<size_t>(nv, 1),
+  const size_t slot = (size_t)std::max(b->n_items, 1) * (size_t)b->stride;   // where the re-solve counter sits
+  cudaError_t e = cudaMemcpyAsync(b->h_values, b->L.out_values, sizeof(double) * (slot + 1),
                                   cudaMemcpyDeviceToHost, ctx->stream);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "D2H");
   ctx->d2h_bytes += (long long)(sizeof(double) * nv);
   e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "kernel execution");
   if (nv > 0) std::memcpy(values, b->h_values, sizeof(double) * nv);
+  unsigned long long rr = 0;
+  std::memcpy(&rr, b->h_values + slot, sizeof rr);
+  b->reruns = (long long)rr;
+  ctx->exact_reruns += (long long)rr;
   return HADI_OK;
 }
 
@@ -877,7 +983,6 @@ int hadi_batch_phase_cycles(hadi_batch* b, long long* out8) {
   if (cudaMemcpy(h.data(), b->L.prof, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost) != cudaSuccess)
     return cuda_fail(b->ctx, cudaGetLastError(), "D2H prof");
   for (int k = 0; k < 8; ++k) out8[k] = 0;
-  b->ctx->exact_reruns = h[(size_t)8 * b->grid_ctas];  // items re-solved with IEEE division since batch creation
   for (int c = 0; c < b->grid_ctas; ++c)
     for (int k = 0; k < 8; ++k) out8[k] += h[(size_t)c * 8 + k];
   return HADI_OK;
@@ -957,6 +1062,7 @@ static int run_items(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics
 int hadi_price_batch(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
                      const hadi_point* points, double* prices, double* U_out, double* lambda_out) {
   if (!ctx || !prices) return HADI_ERR_ARG;
+  if (n < 0 || (n > 0 && !points)) return fail(ctx, HADI_ERR_ARG, "bad argument");
   std::vector<double> vals((size_t)std::max(n, 1));
   const int rc = run_items(ctx, model, num, n, points, HADI_MODE_PRICE, kNoEps, 0, -1, vals.data(), U_out, lambda_out, nullptr);
   if (rc != HADI_OK) return rc;
@@ -990,10 +1096,53 @@ int hadi_jacobian_batch_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nu
                            const hadi_point* points, const hadi_jacobian_options* jo, double* J,
                            double* base_prices) {
   if (!ctx || !J || !base_prices) return HADI_ERR_ARG;
-  if (!model || !valid_numerics(num) || !valid_jopt(jo)) return fail(ctx, HADI_ERR_ARG, "bad argument");
+  if (!model || n < 0 || (n > 0 && !points) || !valid_numerics(num) || !valid_jopt(jo)) return fail(ctx, HADI_ERR_ARG, "bad argument");
   const size_t per_option = (size_t)n_columns(jo->mode) * values_per_item(jo->mode);
   std::vector<double> vals(std::max<size_t>(per_option * n, 1)), Jt((size_t)std::max(5 * n, 1)), bt((size_t)std::max(n, 1));
   int rc = run_items(ctx, model, num, n, points, jo->mode, jo->eps, 0, -1, vals.data(), nullptr, nullptr, nullptr);
+  if (rc != HADI_OK) return rc;
+  int lo, hi;
+  double w = 0.0;
+  hadi_jacobian_v0_weight(num->m2, model->V0, jo->eps[4], &lo, &hi, &w);
+  hadi_jacobian_assemble_ex(n, jo->mode, vals.data(), jo->eps, w, Jt.data(), bt.data());
+  for (int k = 0; k < n; ++k) {
+    const int gi = points[k].global_index;
+    if (gi < 0 || gi >= n) return fail(ctx, HADI_ERR_ARG, "global_index out of range");
+    base_prices[gi] = bt[k];
+    for (int c = 0; c < 5; ++c) J[5 * gi + c] = Jt[5 * k + c];
+  }
+  return HADI_OK;
+}
+
+// One-call entry points over the attached communicator: every rank passes the same arguments, solves its
+// cost-balanced slice of the work items and receives every result (SPMD).
+static int solve_all(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
+                     const hadi_point* points, int mode, const double* eps5, const hadi_comm* comm, double* all,
+                     float* ms);
+
+int hadi_price_batch_sharded(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
+                             const hadi_point* points, double* prices) {
+  if (!ctx || !prices) return HADI_ERR_ARG;
+  if (!model || n < 0 || (n > 0 && !points) || !valid_numerics(num)) return fail(ctx, HADI_ERR_ARG, "bad argument");
+  std::vector<double> vals((size_t)std::max(n, 1));
+  const int rc = solve_all(ctx, model, num, n, points, HADI_MODE_PRICE, kNoEps, nullptr, vals.data(), nullptr);
+  if (rc != HADI_OK) return rc;
+  for (int k = 0; k < n; ++k) {
+    const int gi = points[k].global_index;
+    if (gi < 0 || gi >= n) return fail(ctx, HADI_ERR_ARG, "global_index out of range");
+    prices[gi] = vals[k];
+  }
+  return HADI_OK;
+}
+
+int hadi_jacobian_batch_sharded(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
+                                const hadi_point* points, const hadi_jacobian_options* jo, double* J,
+                                double* base_prices) {
+  if (!ctx || !J || !base_prices) return HADI_ERR_ARG;
+  if (!model || n < 0 || (n > 0 && !points) || !valid_numerics(num) || !valid_jopt(jo)) return fail(ctx, HADI_ERR_ARG, "bad argument");
+  const size_t per_option = (size_t)n_columns(jo->mode) * values_per_item(jo->mode);
+  std::vector<double> vals(std::max<size_t>(per_option * n, 1)), Jt((size_t)std::max(5 * n, 1)), bt((size_t)std::max(n, 1));
+  int rc = solve_all(ctx, model, num, n, points, jo->mode, jo->eps, nullptr, vals.data(), nullptr);
   if (rc != HADI_OK) return rc;
   int lo, hi;
   double w = 0.0;
@@ -1072,6 +1221,66 @@ int hadi_lm_update(int n, const double* J, const double* r, double lambda, doubl
   return hadi_solve5(A, g, delta);
 }
 
+// The same over the context's NCCL communicator, with no host hop in the exchange: this rank's kernel writes its
+// item values straight into its slot of the gather buffer (hadi_publish stores through L.out_values), one in-place
+// ncclAllGather runs behind the kernel on the same stream, one device-to-host copy brings every rank's values back.
+static int solve_all_nccl(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
+                          const hadi_point* points, int mode, const double* eps5, double* all, float* ms) {
+  const int nc = n_columns(mode), vpi = values_per_item(mode);
+  const int total = n * nc, W = ctx->nccl_world, R = ctx->nccl_rank;
+  std::vector<int> costs((size_t)std::max(total, 1)), counts(W), displs(W);
+  hadi_item_costs(num, n, points, mode, costs.data());
+  int my_begin = 0, my_end = 0;
+  size_t mx = 1;
+  for (int r = 0; r < W; ++r) {
+    int b, e;
+    hadi_partition(total, costs.data(), W, r, &b, &e);
+    displs[r] = b * vpi;
+    counts[r] = (e - b) * vpi;
+    mx = std::max(mx, (size_t)counts[r]);
+    if (r == R) { my_begin = b; my_end = e; }
+  }
+  cudaSetDevice(ctx->device);
+  if (ctx->gather_cap < mx) {
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->d_gather) cudaFree(ctx->d_gather);
+    if (ctx->h_gather) cudaFreeHost(ctx->h_gather);
+    ctx->d_gather = nullptr; ctx->h_gather = nullptr; ctx->gather_cap = 0;
+    const size_t cap = std::max<size_t>(mx + mx / 4, 1024);
+    if (cudaMalloc(&ctx->d_gather, sizeof(double) * cap * W) != cudaSuccess ||
+        cudaMallocHost(&ctx->h_gather, sizeof(double) * cap * W) != cudaSuccess)
+      return cuda_fail(ctx, cudaGetLastError(), "gather buffers");
+    ctx->gather_cap = cap;
+  }
+  hadi_batch* b = nullptr;
+  int rc = hadi_batch_create_ex(ctx, model, num, n, points, mode, eps5, my_begin, my_end, &b);
+  if (rc != HADI_OK) return rc;
+  b->L.out_values = ctx->d_gather + (size_t)R * mx;   // the kernel epilogue publishes into the gather buffer
+  rc = hadi_batch_launch(b);
+  if (rc == HADI_OK) {
+    const ncclResult_t nr = nccl_api().AllGather(ctx->d_gather + (size_t)R * mx, ctx->d_gather, mx, ncclDouble,
+                                                 ctx->nccl, ctx->stream);
+    if (nr != ncclSuccess) rc = nccl_fail(ctx, nr, "ncclAllGather");
+  }
+  if (rc == HADI_OK) {
+    cudaError_t e = cudaMemcpyAsync(ctx->h_gather, ctx->d_gather, sizeof(double) * mx * W, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b->h_values, b->L.reruns, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = cuda_fail(ctx, e, "gather D2H");
+    ctx->d2h_bytes += (long long)(sizeof(double) * mx * W);
+  }
+  if (rc == HADI_OK) {
+    for (int r = 0; r < W; ++r)
+      if (counts[r] > 0) std::memcpy(all + displs[r], ctx->h_gather + (size_t)r * mx, sizeof(double) * (size_t)counts[r]);
+    unsigned long long rr = 0;
+    std::memcpy(&rr, b->h_values, sizeof rr);
+    ctx->exact_reruns += (long long)rr;
+    if (ms) hadi_batch_elapsed_ms(b, ms);
+  }
+  hadi_batch_destroy(b);
+  return rc;
+}
+
 // Solve the items of [0, n*nc) across the ranks of `comm` and return every item value on every rank
 // (all[n * nc * values_per_item(mode)]).
 static int solve_all(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
@@ -1079,6 +1288,8 @@ static int solve_all(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics
                      float* ms) {
   const int nc = n_columns(mode), vpi = values_per_item(mode);
   const int total = n * nc;
+  if ((!comm || comm->world <= 1) && ctx->nccl && ctx->nccl_world > 1)
+    return solve_all_nccl(ctx, model, num, n, points, mode, eps5, all, ms);
   if (!comm || comm->world <= 1)
     return run_items(ctx, model, num, n, points, mode, eps5, 0, total, all, nullptr, nullptr, ms);
   std::vector<int> costs((size_t)std::max(total, 1)), counts(comm->world), displs(comm->world);
@@ -1123,6 +1334,7 @@ int hadi_calibrate_ex(hadi_ctx* ctx, const hadi_model* initial, const hadi_numer
   for (int k = 0; k < n; ++k)
     if (points[k].global_index < 0 || points[k].global_index >= n) return fail(ctx, HADI_ERR_ARG, "global_index out of range");
   hadi_model cur = *initial;
+  const long long reruns0 = ctx->exact_reruns;
   double lambda = opt->lambda0;
   std::vector<double> vals((size_t)jcols * values_per_item(jo->mode) * n), J((size_t)5 * n), Jt((size_t)5 * n), base(n), bt(n), r(n), newp(n), nv(n);
   bool converged = false;
@@ -1195,6 +1407,7 @@ int hadi_calibrate_ex(hadi_ctx* ctx, const hadi_model* initial, const hadi_numer
   res->converged = converged ? 1 : 0;
   res->pde_solves = solves;
   res->gpu_ms = gpu_ms;
+  res->exact_reruns = ctx->exact_reruns - reruns0;
   return HADI_OK;
 }
 

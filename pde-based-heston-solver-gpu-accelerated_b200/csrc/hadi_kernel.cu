@@ -14,6 +14,7 @@
 //
 // Compile with -fmad=false: parity with the reference requires un-fused multiplies and adds.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <type_traits>
@@ -98,6 +99,52 @@ __device__ __forceinline__ void hadi_publish(const HadiLaunch& L, const HadiItem
   }
 }
 
+
+// CTA-wide or sub-CTA barrier.  The "duo" variant runs TWO solves per CTA (640 threads, one SM, all 512 columns of
+// tensor memory): threads [0, NT) and [NT, 2 NT) are two independent teams with their own shared-memory working
+// set, item loop and named barrier (bar.sync 1 + team, NT).  id 0 / all threads is __syncthreads().
+struct HadiBar {
+  unsigned id, nt;
+  __device__ __forceinline__ void sync() const {
+    if (id == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nt) : "memory");
+  }
+  __device__ __forceinline__ bool sync_or(int pred) const {
+    if (id == 0) return __syncthreads_or(pred) != 0;
+    unsigned r;
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "setp.ne.s32 p, %3, 0;\n"
+        "bar.red.or.pred q, %1, %2, p;\n"
+        "selp.u32 %0, 1, 0, q;\n"
+        "}\n"
+        : "=r"(r)
+        : "r"(id), "r"(nt), "r"(pred)
+        : "memory");
+    return r != 0;
+  }
+};
+// Turn-taking between the two teams of a duo CTA.  Both teams run the same phase sequence on equal work: left
+// alone they fall into lockstep (explicit stage against explicit stage on the FP64 pipe, line solves against line
+// solves with the pipe idle), which is the worst pairing.  A team takes this lock for its FP64-bound stages, so that
+// one team's explicit stage runs beside the other's latency-bound line solves.
+struct HadiTurn {
+  int* lock;      // shared memory, nullptr: no turn-taking
+  __device__ __forceinline__ void acquire(const HadiBar& bar, int tid) const {
+    if (lock == nullptr) return;
+    if (tid == 0) {
+      while (atomicCAS(lock, 0, 1) != 0) __nanosleep(64);
+    }
+    bar.sync();
+  }
+  // call after the team barrier that ends the stage
+  __device__ __forceinline__ void release(int tid) const {
+    if (lock != nullptr && tid == 0) atomicExch(lock, 0);
+  }
+};
+#define HADI_SYNC() bar.sync()
+
 // One item, payoff to price.  Returns (CTA-uniform) whether any guarded division left its fast-path
 // range; EXACT = true compiles every division as IEEE '/'.
 // FEED == 4: co-operative S1 / pipelined S2 of hadi_phases_fast.cuh (grid-specialised variants only)
@@ -106,12 +153,32 @@ struct HadiCoopFeed : HadiDirectFeed {
 };
 template <class F> struct hadi_is_coop { static constexpr bool value = false; };
 template <> struct hadi_is_coop<HadiCoopFeed> { static constexpr bool value = true; };
+// FEED == 5: back-substitution factors of S1 in tensor memory (hadi_phases_fast.cuh)
+struct HadiTmemFeed : HadiDirectFeed {
+  unsigned tmem = 0;        // base address of the CTA's tensor-memory allocation
+  double* dummy = nullptr;  // a row of shared memory nobody reads (lanes that are not live in a half sweep)
+};
+template <class F> struct hadi_is_tmem { static constexpr bool value = false; };
+template <> struct hadi_is_tmem<HadiTmemFeed> { static constexpr bool value = true; };
+// FEED == 6: the whole S1 factor stream in tensor memory, one lane per v-row (duo kernel: 512 columns per CTA)
+struct HadiTmem2Feed : HadiDirectFeed {
+  unsigned tmem = 0;
+  int wbase = 0;   // first of the team's two chain warps (team-local index)
+};
+// FEED == 7: back-substitution stream in tensor memory, relayed from warps 0, 1 to warps 2, 3 (two CTAs per SM)
+struct HadiRelayFeed : HadiDirectFeed {
+  unsigned tmem = 0;
+};
+template <class F> struct hadi_is_relay { static constexpr bool value = false; };
+template <> struct hadi_is_relay<HadiRelayFeed> { static constexpr bool value = true; };
+template <class F> struct hadi_is_tmem2 { static constexpr bool value = false; };
+template <> struct hadi_is_tmem2<HadiTmem2Feed> { static constexpr bool value = true; };
 
 // n0..n1: the time steps to run (1..N for a whole solve); hin: state to resume from (nullptr: start from the payoff)
 template <int NT, int M1, int M2, bool EXACT, class Feed>
 __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiItem& it, HadiView& w, Feed& feed,
                                                 int tid, long long* tacc, long long& tlast, int n0, int n1,
-                                                const double* hin) {
+                                                const double* hin, const HadiBar& bar, const HadiTurn& turn = HadiTurn{nullptr}) {
   const int m1 = M1 ? M1 : L.m1, m2 = M2 ? M2 : L.m2;
   const double* sg = L.s_pool + it.s_off;
   const double* vg = L.v_pool + it.v_off;
@@ -126,8 +193,19 @@ __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiI
     if (tid < 2 * hadi_co_warps(M2))
       reinterpret_cast<int*>(w.stg + hadi_co_warps(M2) * hadi_co_warp_doubles())[tid] = 0;
   }
-  __syncthreads();
-  hadi_phase_factor(it, w, vg, tid, NT, NT - 1);
+  HADI_SYNC();
+  if constexpr (hadi_is_tmem<Feed>::value && M1 > 0) {
+    hadi_phase_factor(it, w, vg, tid, NT, NT - 1, false);   // A2 only; the A1 rows go to tensor memory
+    hadi_tmem_factor<M1, M2>(it, w, vg, tid, feed.tmem);
+  } else if constexpr (hadi_is_tmem2<Feed>::value && M1 > 0) {
+    hadi_phase_factor(it, w, vg, tid, NT, NT - 1, false);
+    hadi_tmem2_factor<M1, M2>(it, w, vg, tid, feed.tmem, feed.wbase);
+  } else if constexpr (hadi_is_relay<Feed>::value && M1 > 0) {
+    hadi_phase_factor(it, w, vg, tid, NT, NT - 1, false);
+    hadi_relay_factor<M1, M2>(it, w, vg, tid, feed.tmem);
+  } else {
+    hadi_phase_factor(it, w, vg, tid, NT, NT - 1);
+  }
   if constexpr (Feed::kTma) {
     // the factor streams were written with generic stores and will be read by TMA (async proxy)
 #ifndef HADI_NO_THREADFENCE
@@ -135,7 +213,7 @@ __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiI
 #endif
     asm volatile("fence.proxy.async;" ::: "memory");
   }
-  __syncthreads();  // the A2 assembly keeps scratch tables in Y: finish it before Y is initialised
+  HADI_SYNC();  // the A2 assembly keeps scratch tables in Y: finish it before Y is initialised
   // initial condition U = payoff (the reference's U_0 input array), lambda = 0 — or the state another CTA
   // left after step n0 - 1 (split schedule)
   {
@@ -162,7 +240,7 @@ __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiI
     }
   }
   if constexpr (hadi_is_coop<Feed>::value && M1 > 0) hadi_fast_prestage<M1, M2>(w, tid, 0);
-  __syncthreads();
+  HADI_SYNC();
   if constexpr (Feed::kTma) {
     if (feed.producer(tid)) feed.produce(0, it.N, 0);  // first chunks are in flight before step 1
   }
@@ -178,14 +256,14 @@ __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiI
       const int hit = hadi_dividend_at(n, it.dt, it.nd, L.div_dates, div_cur);
       if (hit >= 0) {  // uniform across the CTA
         hadi_phase_div1(w, L.div_amounts[hit], L.div_pcts[hit], tid, NT);
-        __syncthreads();
+        HADI_SYNC();
         HADI_STOP(1)
         hadi_phase_div2(w, tid, NT);
-        __syncthreads();
+        HADI_SYNC();
         HADI_STOP(2)
         if (it.style == 1) {
           hadi_phase_div3(w, tid, NT);
-          __syncthreads();
+          HADI_SYNC();
         }
         HADI_STOP(3)
       }
@@ -195,25 +273,33 @@ __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiI
     if (it.style == 1) hadi_dbg_check_lam(L, w, n, it.out, tid, NT);
 #endif
     const double e0 = eg[n - 1], e1 = eg[n];
+    turn.acquire(bar, tid);
     hadi_phase_explicit<M1, M2>(it, w, e0, e1, tid, NT);
-    __syncthreads();
+    HADI_SYNC();
+    turn.release(tid);
     HADI_TICK(2)
     HADI_STOP(4)
     if constexpr (hadi_is_coop<Feed>::value && M1 > 0) {
       hadi_fast_solve_a1<M1, M2, EXACT>(it, w, n - 1, tid, bad, &tacc[1]);
+    } else if constexpr (hadi_is_tmem<Feed>::value && M1 > 0) {
+      hadi_tmem_solve_a1<M1, M2, EXACT>(it, w, tid, bad, feed.tmem, feed.dummy, &tacc[1]);
+    } else if constexpr (hadi_is_tmem2<Feed>::value && M1 > 0) {
+      hadi_tmem2_solve_a1<M1, M2, EXACT>(it, w, tid, bad, feed.tmem, feed.wbase, &tacc[1]);
+    } else if constexpr (hadi_is_relay<Feed>::value && M1 > 0) {
+      hadi_relay_solve_a1<M1, M2, EXACT>(it, w, tid, bad, feed.tmem, &tacc[1]);
     } else {
       hadi_phase_solve_a1<M1, M2, EXACT>(it, w, e0, e1, n, tid, NT, feed, bad, &tacc[1]);
     }
-    __syncthreads();
+    HADI_SYNC();
     HADI_TICK(3)
     HADI_STOP(5)
 #ifdef HADI_SPLIT_R
     hadi_phase_rhs2<M1, M2>(it, w, e0, e1, tid, NT);
-    __syncthreads();
+    HADI_SYNC();
 #else
     if constexpr (M1 == 0) {
       hadi_phase_rhs2<M1, M2>(it, w, e0, e1, tid, NT);
-      __syncthreads();
+      HADI_SYNC();
     }
 #endif
     HADI_TICK(7)
@@ -227,14 +313,16 @@ __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiI
     } else {
       hadi_phase_solve_a2<M1, M2, EXACT>(it, w, tid, NT, bad);
     }
-    __syncthreads();
+    HADI_SYNC();
     HADI_TICK(4)
     HADI_STOP(7)
     if (it.style == 1) {
       // all multiplier loads of a thread's rows are issued before the first is used (one L2 round trip)
-      constexpr int CHP = (M1 == 100 && M2 == 50 && NT / 101 == 3) ? 17 : HADI_CHP;
+      constexpr int CHP = (M1 == 100 && M2 == 50 && NT / 101 == 3) ? 17 : (M1 == 100 && M2 == 50 && NT / 101 == 2) ? 13 : HADI_CHP;
+      if (L.flags & 2) turn.acquire(bar, tid);
       hadi_phase_project<M1, M2, EXACT, CHP>(it, w, rdt, tid, NT, bad);
-      __syncthreads();
+      HADI_SYNC();
+      if (L.flags & 2) turn.release(tid);
     }
     HADI_TICK(5)
     HADI_STOP(8)
@@ -245,7 +333,7 @@ __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiI
       // drain the chunks the producer had in flight so that the ring counters stay consistent
       __shared__ unsigned s_issued;
       if (feed.producer(tid)) s_issued = feed.issued;
-      __syncthreads();
+      HADI_SYNC();
       const unsigned upto = s_issued;
       if (tid <= m2) {
         while (feed.consumed != upto) {
@@ -256,7 +344,7 @@ __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiI
         }
       }
       feed.issued = feed.consumed = feed.base = upto;
-      __syncthreads();
+      HADI_SYNC();
     } else
 #endif
     {
@@ -266,13 +354,13 @@ __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiI
     }
   }
   (void)stopped;
-  return __syncthreads_or((int)bad) != 0;
+  return bar.sync_or((int)bad);
 }
 
 // Craig-Sneyd (European, no dividends) on the global-state working set: src/solver.hpp:781-907.
 template <int NT, bool EXACT, class Feed>
 __device__ __forceinline__ bool hadi_solve_item_cs(const HadiLaunch& L, const HadiItem& it, HadiView& w,
-                                                   const HadiCsView& cs, Feed& feed, int tid) {
+                                                   const HadiCsView& cs, Feed& feed, int tid, const HadiBar& bar) {
   const int m1 = L.m1, m2 = L.m2;
   const double* sg = L.s_pool + it.s_off;
   const double* vg = L.v_pool + it.v_off;
@@ -280,13 +368,13 @@ __device__ __forceinline__ bool hadi_solve_item_cs(const HadiLaunch& L, const Ha
   w.c = it.theta * it.dt;
   unsigned bad = 0;
   hadi_phase_tables(it, w, sg, vg, tid, NT);
-  __syncthreads();
+  HADI_SYNC();
   hadi_phase_factor(it, w, vg, tid, NT, NT - 1);
   if constexpr (Feed::kTma) {
     __threadfence();
     asm volatile("fence.proxy.async;" ::: "memory");
   }
-  __syncthreads();
+  HADI_SYNC();
   {
     const HadiMap mp = hadi_map(m1, m2, tid, NT);
     if (mp.active) {
@@ -294,7 +382,7 @@ __device__ __forceinline__ bool hadi_solve_item_cs(const HadiLaunch& L, const Ha
       for (int j = mp.j0; j < mp.j1; ++j) w.U[j * w.ld + mp.i] = pay;
     }
   }
-  __syncthreads();
+  HADI_SYNC();
   // two A1 solves per step: the feed sees 2N "steps"
   if constexpr (Feed::kTma) {
     if (feed.producer(tid)) feed.produce(0, 2 * it.N, 0);
@@ -303,34 +391,45 @@ __device__ __forceinline__ bool hadi_solve_item_cs(const HadiLaunch& L, const Ha
   for (int n = 1; n <= it.N; ++n) {
     const double e0 = eg[n - 1], e1 = eg[n];
     hadi_cs_predict(it, w, cs, e0, e1, tid, NT);
-    __syncthreads();
+    HADI_SYNC();
     hadi_phase_solve_a1<0, 0, EXACT>(it, w, e0, e1, 2 * n - 1, tid, NT, feed, bad, nullptr, 2 * it.N);
-    __syncthreads();
+    HADI_SYNC();
     hadi_cs_rhs2(it, w, cs, e0, e1, tid, NT);
-    __syncthreads();
+    HADI_SYNC();
     hadi_phase_solve_a2<0, 0, EXACT>(it, w, tid, NT, bad);   // Y2 -> U
-    __syncthreads();
+    HADI_SYNC();
     hadi_cs_correct(it, w, cs, e0, e1, tid, NT);
-    __syncthreads();
+    HADI_SYNC();
     hadi_phase_solve_a1<0, 0, EXACT>(it, w, e0, e1, 2 * n, tid, NT, feed, bad, nullptr, 2 * it.N);
-    __syncthreads();
+    HADI_SYNC();
     hadi_cs_rhs2(it, w, cs, e0, e1, tid, NT);
-    __syncthreads();
+    HADI_SYNC();
     hadi_phase_solve_a2<0, 0, EXACT>(it, w, tid, NT, bad);
-    __syncthreads();
+    HADI_SYNC();
   }
   if constexpr (Feed::kTma) {
     const unsigned nc = (unsigned)(feed.ncf() + feed.ncb());
     feed.issued = feed.consumed = feed.base = feed.base + (unsigned)(2 * it.N) * nc;
   }
-  return __syncthreads_or((int)bad) != 0;
+  return bar.sync_or((int)bad);
 }
 
-template <int NT, int MINB, int M1, int M2, int FEED, bool GLOBAL = false>
-__global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch L) {
+// DUO: solves in flight per CTA (teams of NT threads; see HadiBar).  Team t of CTA b is "virtual block" b*DUO + t:
+// scratch slot, segment list and profile slot are indexed by it, L.vgrid is their count.
+template <int NT, int MINB, int M1, int M2, int FEED, bool GLOBAL = false, int DUO = 1>
+__global__ void __launch_bounds__(NT * DUO, MINB) hadi_douglas_kernel(const HadiLaunch L) {
   extern __shared__ double smem[];
-  __shared__ int s_item;
-  const int tid = threadIdx.x;
+  __shared__ int s_item_team[DUO];
+  const int team = (DUO > 1) ? (int)threadIdx.x / NT : 0;
+  const int tid = (int)threadIdx.x - team * NT;
+  // team 0 of every CTA is served first: a batch of up to one solve per SM keeps the second teams idle
+  const int vb = team * (int)gridDim.x + (int)blockIdx.x;
+  const int vgrid = (DUO > 1) ? L.vgrid : (int)gridDim.x;
+  __shared__ int s_turn;
+  if (threadIdx.x == 0) s_turn = 0;
+  const HadiTurn turn{(DUO > 1 && (L.flags & 1)) ? &s_turn : nullptr};
+  int& s_item = s_item_team[team];
+  const HadiBar bar{(DUO > 1) ? 1u + (unsigned)team : 0u, (unsigned)NT};
   long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long tlast = 0;
 #ifdef HADI_PHASE_TIMING
@@ -341,15 +440,15 @@ __global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch
   HadiView w;
   w.m1 = m1; w.m2 = m2; w.P = (m1 + 1) * (m2 + 1);
   w.ld = hadi_geo_ld(m1); w.n1 = hadi_geo_n1(m1); w.n2 = hadi_geo_n2(m2); w.pj = hadi_geo_pj(m2);
-  const HadiSmemLayout lay = hadi_smem_layout(m1, m2, w.ld, w.n1, w.n2, w.pj, FEED == 1, GLOBAL, FEED == 4, M1 > 0);
+  const HadiSmemLayout lay = hadi_smem_layout(m1, m2, w.ld, w.n1, w.n2, w.pj, FEED == 1, GLOBAL, FEED == 4, M1 > 0, FEED == 5);
   if constexpr (M1 > 0) w.nti = HADI_LEAN ? TI_CORE : TI_COUNT;
-  char* sbase = reinterpret_cast<char*>(smem);
+  char* sbase = reinterpret_cast<char*>(smem) + (size_t)team * ((lay.total + 127) & ~size_t(127));
   w.zmask = (L.n_items < 0) ? ~0u : 0u;   // a zero the compiler cannot fold
   if constexpr (FEED == 4) {
     w.co_pi = hadi_co_pi(m1);
     w.stg = reinterpret_cast<double*>(sbase + lay.ring);
   }
-  double* scratch = L.scratch + (size_t)blockIdx.x * L.scratch_stride;
+  double* scratch = L.scratch + (size_t)(vb < vgrid ? vb : 0) * L.scratch_stride;
   const HadiScratchLayout gl = hadi_scratch_layout(m1, m2, w.ld, w.pj, GLOBAL, GLOBAL && L.scheme == 1);
   // the working set: shared memory, or (GLOBAL) L2-resident global scratch for grids beyond it
   double* Ualloc = GLOBAL ? scratch + gl.U : reinterpret_cast<double*>(sbase + lay.U);
@@ -373,13 +472,28 @@ __global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch
   //       4 co-operative warps (hadi_phases_fast.cuh)
   typename std::conditional<FEED == 1, HadiRingFeed,
       typename std::conditional<FEED == 3, HadiPrefetchFeed,
-          typename std::conditional<FEED == 4, HadiCoopFeed, HadiDirectFeed>::type>::type>::type feed;
+          typename std::conditional<FEED == 4, HadiCoopFeed,
+              typename std::conditional<FEED == 5, HadiTmemFeed,
+                  typename std::conditional<FEED == 6, HadiTmem2Feed,
+                      typename std::conditional<FEED == 7, HadiRelayFeed, HadiDirectFeed>::type>::type>::type>::type>::type>::type feed;
   feed.fM = w.fM;
   feed.fB = w.fB;
   feed.pj = w.pj;
   if constexpr (FEED == 3) {
     feed.m1 = m1;
     feed.j = 0;
+  }
+  if constexpr (FEED == 5) {
+    // tensor memory: 256 (101 x 51) / 128 (51 x 26) columns per CTA, held until the CTA exits
+    static_assert(M1 > 0, "the tensor-memory feed exists for the grid-specialised variants only");
+    __shared__ unsigned s_tmem;
+    if (tid < 32) hadi_tm_alloc(&s_tmem, hadi_tm_cols(M1));
+    hadi_tm_fence_before();
+    HADI_SYNC();
+    hadi_tm_fence_after();
+    feed.tmem = s_tmem;
+    feed.dummy = reinterpret_cast<double*>(sbase + lay.ring);
+    for (int k = tid; k < m1 + 2; k += NT) feed.dummy[k] = 0.0;
   }
   if constexpr (FEED == 1) {
     feed.m1 = m1;
@@ -401,23 +515,24 @@ __global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
   }
-  __syncthreads();
+  HADI_SYNC();
 
   // Work source: whole items pulled from a global counter, or (split schedule) this CTA's static list of
   // segments — McNaughton's wrap-around rule on the host cuts the one solve that straddles the end of a CTA's
   // share of the batch in two, so that every CTA finishes at the same time instead of after a whole number of
   // solves (hadi_host.cpp: build_split_schedule).
   const bool split = (L.segs != nullptr) && !GLOBAL && FEED != 1 && FEED != 4;
-  int seg_q = split ? L.seg_off[blockIdx.x] : 0;
-  const int seg_end = split ? L.seg_off[blockIdx.x + 1] : 0;
+  int seg_q = (split && vb < vgrid) ? L.seg_off[vb] : 0;
+  const int seg_end = (split && vb < vgrid) ? L.seg_off[vb + 1] : 0;
   for (;;) {
+    if (DUO > 1 && vb >= vgrid) break;   // a team beyond the virtual grid (odd number of work slots) has nothing to do
     HadiSegment sg;
     if (split) {
       if (seg_q >= seg_end) break;
       sg = L.segs[seg_q++];
     } else {
       if (tid == 0) s_item = atomicAdd(L.counter, 1);
-      __syncthreads();
+      HADI_SYNC();
       sg.item = s_item;
       if (sg.item >= L.n_items) break;
       sg.n0 = 1; sg.n1 = 0; sg.hin = -1; sg.hout = -1;
@@ -443,37 +558,37 @@ __global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch
         }
         s_item = st;
       }
-      __syncthreads();
+      HADI_SYNC();
       if (s_item == HADI_HAND_READY) hin = L.hand_data + (size_t)sg.hin * 2 * (size_t)w.P;
       else whole_exact = true;
-      __syncthreads();
+      HADI_SYNC();
     }
     // fast pass; if any guarded division left its range (never observed on option data at these grids), the
     // item is re-solved with IEEE divisions so that the published value is exact in every case
     bool cs_done = false;
     if constexpr (GLOBAL) {
       if (L.scheme == 1) {
-        if (hadi_solve_item_cs<NT, false>(L, it, w, cs, feed, tid)) hadi_solve_item_cs<NT, true>(L, it, w, cs, feed, tid);
+        if (hadi_solve_item_cs<NT, false>(L, it, w, cs, feed, tid, bar)) hadi_solve_item_cs<NT, true>(L, it, w, cs, feed, tid, bar);
         cs_done = true;
       }
     }
     if (!cs_done) {
 #ifdef HADI_FORCE_EXACT
-      if (!whole_exact) hadi_solve_item<NT, M1, M2, true>(L, it, w, feed, tid, tacc, tlast, sg.n0, sg.n1, hin);
+      if (!whole_exact) hadi_solve_item<NT, M1, M2, true>(L, it, w, feed, tid, tacc, tlast, sg.n0, sg.n1, hin, bar, turn);
 #else
       if (!whole_exact) {
 #ifdef HADI_NO_RERUN   /* timing experiments only */
-        whole_exact = hadi_solve_item<NT, M1, M2, false>(L, it, w, feed, tid, tacc, tlast, sg.n0, sg.n1, hin) && L.n_items < 0;
+        whole_exact = hadi_solve_item<NT, M1, M2, false>(L, it, w, feed, tid, tacc, tlast, sg.n0, sg.n1, hin, bar, turn) && L.n_items < 0;
 #else
-        whole_exact = hadi_solve_item<NT, M1, M2, false>(L, it, w, feed, tid, tacc, tlast, sg.n0, sg.n1, hin);
+        whole_exact = hadi_solve_item<NT, M1, M2, false>(L, it, w, feed, tid, tacc, tlast, sg.n0, sg.n1, hin, bar, turn);
 #endif
       }
 #endif
       if (L.dbg_step == -7) whole_exact = true;   // test hook (HADI_DEBUG_STOP=-7:0): treat every fast pass as out of range
       if (whole_exact) {
-        if (tid == 0 && L.prof != nullptr) atomicAdd((unsigned long long*)&L.prof[(size_t)gridDim.x * 8], 1ULL);
+        if (tid == 0 && L.reruns != nullptr) atomicAdd(L.reruns, 1ULL);
         // only the CTA that holds the last steps publishes: it re-solves the whole item
-        if (sg.hout < 0) hadi_solve_item<NT, M1, M2, true>(L, it, w, feed, tid, tacc, tlast, 1, it.N, nullptr);
+        if (sg.hout < 0) hadi_solve_item<NT, M1, M2, true>(L, it, w, feed, tid, tacc, tlast, 1, it.N, nullptr, bar, turn);
       }
     }
 
@@ -490,13 +605,13 @@ __global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch
           }
         }
       }
-      __syncthreads();
+      HADI_SYNC();
       if (tid == 0) {
         __threadfence();
         const int st = whole_exact ? HADI_HAND_BAD : HADI_HAND_READY;
         asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(L.hand_state + sg.hout), "r"(st) : "memory");
       }
-      __syncthreads();
+      HADI_SYNC();
       HADI_TICK(6)
       continue;
     }
@@ -522,13 +637,18 @@ __global__ void __launch_bounds__(NT, MINB) hadi_douglas_kernel(const HadiLaunch
         }
       }
     }
-    __syncthreads();  // everyone is done with s_item, U and the tables before the next item
+    HADI_SYNC();  // everyone is done with s_item, U and the tables before the next item
     HADI_TICK(6)
+  }
+  if constexpr (FEED == 5) {
+    hadi_tm_fence_before();
+    HADI_SYNC();
+    if (tid < 32) hadi_tm_free(feed.tmem, hadi_tm_cols(M1));
   }
 #ifdef HADI_PHASE_TIMING
   if constexpr (FEED == 1) tacc[6] = feed.wait_cycles;   // slot 6 reports the ring wait of solver thread 0
-  if (tid == 0 && L.prof != nullptr)
-    for (int k = 0; k < 8; ++k) L.prof[(size_t)blockIdx.x * 8 + k] = tacc[k];
+  if (tid == 0 && L.prof != nullptr && vb < vgrid)
+    for (int k = 0; k < 8; ++k) L.prof[(size_t)vb * 8 + k] = tacc[k];
 #endif
 }
 
@@ -656,7 +776,7 @@ __global__ void __cluster_dims__(HADI_CLUSTER, 1, 1) __launch_bounds__(NT, 1) ha
     if (item >= L.n_items) break;
     const HadiItem it = L.items[item];
     if (hadi_cluster_solve<NT, false>(L, it, w, cs, tid, gtid, gnt, mail)) {
-      if (gtid == 0 && L.prof != nullptr) atomicAdd((unsigned long long*)&L.prof[(size_t)gridDim.x * 8], 1ULL);
+      if (gtid == 0 && L.reruns != nullptr) atomicAdd(L.reruns, 1ULL);
       hadi_cluster_solve<NT, true>(L, it, w, cs, tid, gtid, gnt, mail);
     }
     if (gtid == 0) hadi_publish(L, it, w);
@@ -694,31 +814,48 @@ __global__ void __cluster_dims__(HADI_CLUSTER, 1, 1) __launch_bounds__(NT, 1) ha
 #ifndef HADI_FEED1
 #define HADI_FEED1 3
 #endif
-#define HADI_VARIANTS(X)                 \
-  X(0, 320, 2, 100, 50, HADI_FEED0, false) \
-  X(1, 256, 3, 50, 25, HADI_FEED1, false)  \
-  X(2, 416, 2, 0, 0, 0, false)          \
-  X(3, 1024, 1, 0, 0, 0, false)         \
-  X(4, 320, 2, 100, 50, 4, false)       \
-  X(5, 512, 1, 0, 0, 1, true)           \
-  X(6, 1024, 1, 0, 0, 1, true)
+#ifndef HADI_DUO_NT
+#define HADI_DUO_NT 320   /* threads per team of the duo kernel (2 x 256 threads with 128 registers each measured slower) */
+#endif
+#ifndef HADI_DUO
+#define HADI_DUO 1   /* 0: variant 8 (two solves per CTA, S1 out of tensor memory) is never chosen by the planner */
+#endif
+// X(id, threads per team, min CTAs/SM, m1, m2, feed, global state, teams per CTA)
+#define HADI_VARIANTS(X)                    \
+  X(0, 320, 2, 100, 50, HADI_FEED0, false, 1) \
+  X(1, 256, 3, 50, 25, HADI_FEED1, false, 1)  \
+  X(2, 416, 2, 0, 0, 0, false, 1)          \
+  X(3, 1024, 1, 0, 0, 0, false, 1)         \
+  X(4, 320, 2, 100, 50, 4, false, 1)       \
+  X(5, 512, 1, 0, 0, 1, true, 1)           \
+  X(6, 1024, 1, 0, 0, 1, true, 1)          \
+  X(8, HADI_DUO_NT, 1, 100, 50, 6, false, 2)
 
 struct VariantInfo {
-  int threads, m1, m2;
-  int feed;   // 0 plain loads, 1 TMA ring, 3 plain loads behind L1 prefetches, 4 co-operative warps
+  int id;
+  int threads, minb, m1, m2;
+  int feed;   // 0 plain loads, 1 TMA ring, 3 plain loads behind L1 prefetches, 4 co-operative warps, 5 / 6 tensor memory
   bool global_state;
+  int duo;    // teams (solves in flight) per CTA
   const void* fn;
 };
 const VariantInfo* variants() {
   static const VariantInfo v[] = {
-#define X(id, nt, minb, a, b, r, g) {nt, a, b, r, g, (const void*)hadi_douglas_kernel<nt, minb, a, b, r, g>},
+#define X(id, nt, minb, a, b, r, g, d) {id, nt, minb, a, b, r, g, d, (const void*)hadi_douglas_kernel<nt, minb, a, b, r, g, d>},
       HADI_VARIANTS(X)
 #undef X
   };
   return v;
 }
-constexpr int kNumVariants = 7;
+constexpr int kNumVariants = 8;      // entries of the table above
 constexpr int kClusterVariant = 7;   // hadi_cluster_kernel: one solve per thread-block cluster
+constexpr int kDuoVariant = 8;
+const VariantInfo* variant_by_id(int id) {
+  const VariantInfo* v = variants();
+  for (int k = 0; k < kNumVariants; ++k)
+    if (v[k].id == id) return &v[k];
+  return nullptr;
+}
 constexpr int kClusterThreads = 256; // few threads, many registers: the generic phases spill badly at 64 registers
 
 }  // namespace
@@ -755,48 +892,80 @@ int hadi_douglas_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj
   }
   // development aid: HADI_FORCE_VARIANT=<id> restricts the choice (e.g. 2 = run-time dims, direct loads)
   const char* force = getenv("HADI_FORCE_VARIANT");
-  for (int k = 0; k < kNumVariants; ++k) {
-    if (force && atoi(force) != k) continue;
-    if (need_global && !v[k].global_state) continue;
-    if (v[k].m1 != 0 && (v[k].m1 != m1 || v[k].m2 != m2)) continue;
-    if (v[k].threads < m1 + 1 || v[k].threads - 1 <= m2) continue;
-    if (v[k].feed == 1 && v[k].threads <= 32 * ((m2 + 1 + 31) / 32)) continue;   // needs a producer thread past the solver warps
-    smem = hadi_smem_layout(m1, m2, ld, n1, n2, pj, v[k].feed == 1, v[k].global_state, v[k].feed == 4, v[k].m1 != 0).total;
-    if (smem > (size_t)max_smem) continue;
-    pick = k;
-    break;
+  const char* noduo = getenv("HADI_NO_DUO");
+  auto eligible = [&](const VariantInfo& q, size_t* bytes) -> bool {
+    if (force && atoi(force) != q.id) return false;
+    if (need_global && !q.global_state) return false;
+    if (q.m1 != 0 && (q.m1 != m1 || q.m2 != m2)) return false;
+    if (q.threads < m1 + 1 || q.threads - 1 <= m2) return false;
+    if (q.feed == 1 && q.threads <= 32 * ((m2 + 1 + 31) / 32)) return false;   // needs a producer thread past the solver warps
+    const size_t one = hadi_smem_layout(m1, m2, ld, n1, n2, pj, q.feed == 1, q.global_state, q.feed == 4, q.m1 != 0, q.feed == 5).total;
+    *bytes = q.duo > 1 ? (size_t)q.duo * ((one + 127) & ~size_t(127)) : one;
+    return *bytes <= (size_t)max_smem;
+  };
+  // first choice where it exists: two solves per CTA with phase S1 fed from tensor memory (variant 8)
+  if (HADI_DUO && !(noduo && atoi(noduo) != 0)) {
+    for (int k = 0; k < kNumVariants && pick < 0; ++k)
+      if (v[k].duo > 1 && eligible(v[k], &smem)) pick = k;
+  }
+  for (int k = 0; k < kNumVariants && pick < 0; ++k) {
+    if (v[k].duo > 1 && !(force && atoi(force) == v[k].id)) continue;
+    if (eligible(v[k], &smem)) pick = k;
   }
   if (pick < 0) return -1;
   e = cudaFuncSetAttribute(v[pick].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v[pick].fn, v[pick].threads, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v[pick].fn, v[pick].threads * v[pick].duo, smem);
   if (e != cudaSuccess) return (int)e;
   if (occ < 1) return -1;
+  if (v[pick].feed == 5 || v[pick].feed == 7) {
+    // The occupancy calculator knows nothing about tensor memory and answers 1 for a kernel that executes
+    // tcgen05.alloc; the hardware co-schedules CTAs as long as registers and shared memory fit, and each CTA's
+    // allocation of hadi_tm_cols() columns then succeeds while the SM's 512 columns last (measured on B200
+    // with tools/ubench_tmem.cu: two CTAs x 256 columns resident on all 148 SMs).  Residency from the launch
+    // bounds (registers), the shared-memory footprint and the column budget:
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, v[pick].fn);
+    if (e != cudaSuccess) return (int)e;
+    int smem_sm = 0, regs_sm = 0;
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
+    cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, device);
+    const int by_smem = (int)((size_t)smem_sm / (smem + fa.sharedSizeBytes + 1024));
+    const int by_regs = regs_sm / (((fa.numRegs + 7) & ~7) * v[pick].threads);
+    const int by_tmem = 512 / hadi_tm_cols_feed(v[pick].feed, v[pick].m1);
+    occ = std::min(std::min(by_smem, by_regs), std::min(by_tmem, v[pick].minb));
+    if (occ < 1) return -1;
+  }
+  if (v[pick].feed == 6) occ = 1;   // the CTA owns all 512 tensor-memory columns of its SM
   plan->global_state = v[pick].global_state;
-  plan->variant = pick;
-  plan->threads = v[pick].threads;
-  plan->ctas_per_sm = occ;
+  plan->variant = v[pick].id;
+  plan->threads = v[pick].threads * v[pick].duo;
+  plan->ctas_per_sm = occ * v[pick].duo;   // work slots (solves in flight) per SM
   plan->sm_count = sms;
   plan->smem_bytes = smem;
   plan->cluster = 1;
+  plan->duo = v[pick].duo;
   return 0;
 }
 
-int hadi_launch_douglas(const HadiLaunch& L, const HadiPlan& plan, int grid_ctas, void* stream) {
+int hadi_launch_douglas(const HadiLaunch& L_in, const HadiPlan& plan, int grid_ctas, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  HadiLaunch L = L_in;
+  L.vgrid = grid_ctas;   // work slots; the duo kernel packs two per CTA
   // the run-time-dimension kernels serve many grid shapes and plans are cached by the host layer: the dynamic
   // shared-memory limit of the function must be the one of THIS plan, not of the plan made last
   {
-    const void* fn = plan.variant == kClusterVariant ? (const void*)hadi_cluster_kernel<kClusterThreads>
-                                                     : variants()[plan.variant].fn;
+    const VariantInfo* q = variant_by_id(plan.variant);
+    if (plan.variant != kClusterVariant && q == nullptr) return (int)cudaErrorInvalidValue;
+    const void* fn = plan.variant == kClusterVariant ? (const void*)hadi_cluster_kernel<kClusterThreads> : q->fn;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes);
     if (e != cudaSuccess) return (int)e;
   }
   switch (plan.variant) {
-#define X(id, nt, minb, a, b, r, g) \
-  case id:                          \
-    hadi_douglas_kernel<nt, minb, a, b, r, g><<<grid_ctas, nt, plan.smem_bytes, st>>>(L); \
+#define X(id, nt, minb, a, b, r, g, d) \
+  case id:                             \
+    hadi_douglas_kernel<nt, minb, a, b, r, g, d><<<d > 1 ? std::min(grid_ctas, std::max(plan.sm_count, (grid_ctas + d - 1) / d)) : grid_ctas, nt * d, plan.smem_bytes, st>>>(L); \
     break;
     HADI_VARIANTS(X)
 #undef X

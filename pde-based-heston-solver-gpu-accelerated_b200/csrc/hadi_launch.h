@@ -13,6 +13,7 @@
 struct HadiSegment {
   int item, n0, n1, hin, hout, pad0, pad1, pad2;
 };
+#define HADI_FLAGS_DEFAULT 1
 #define HADI_HAND_PENDING 0
 #define HADI_HAND_READY 1
 #define HADI_HAND_BAD 2      /* a guarded division left its range: the final segment re-solves the whole item with IEEE '/' */
@@ -35,7 +36,9 @@ struct HadiLaunch {
   int out_stride;            // values per item: 1, or 3 = {price, U(S0, v_lower), U(S0, v_upper)} (interpolated-V0 Jacobian)
   double* out_U;             // optional [n_items][P] natural layout
   double* out_lam;           // optional [n_items][P]
-  long long* prof;           // optional [gridDim.x][8] phase cycle counters (HADI_PHASE_TIMING builds only)
+  long long* prof;           // optional [work slots][8] phase cycle counters (HADI_PHASE_TIMING builds only)
+  unsigned long long* reruns;  // items of this launch re-solved with IEEE divisions (guarded division left its range,
+                             // or a hand-off timed out); zeroed before the launch, read back with the values
   int dbg_step, dbg_phase;   // HADI_DEBUG_STOP builds only: end every item after phase dbg_phase of step dbg_step
   int scheme;                // 0 Douglas, 1 Craig-Sneyd (global-state kernel only)
   // split schedule (nullptr: CTAs pull whole items from `counter`): CTA b runs segs[seg_off[b] .. seg_off[b+1])
@@ -43,6 +46,9 @@ struct HadiLaunch {
   const int* seg_off;        // [gridDim.x + 1]
   int* hand_state;           // [n_hand] HADI_HAND_* (zeroed before launch)
   double* hand_data;         // [n_hand][2 * P]: U then lambda, natural layout
+  int flags;                 // scheduling switches (HADI_FLAGS, default HADI_FLAGS_DEFAULT): bit 0 — in the duo kernel the two
+                             // teams of a CTA take turns in the FP64-bound explicit stage; bit 1 — and in the projection
+  int vgrid;                 // work slots of this launch (set by hadi_launch_douglas; = CTAs except in the duo kernel)
 };
 
 // Kernel variant chosen for a grid shape (hadi_kernel.cu).
@@ -54,6 +60,7 @@ struct HadiPlan {
   int sm_count;
   size_t smem_bytes;  // dynamic shared memory per CTA
   int cluster;        // CTAs that share one solve (1, or HADI_CLUSTER in the cluster kernel)
+  int duo = 1;        // solves in flight per CTA (2 in the duo kernel; ctas_per_sm counts work slots)
 };
 
 // shared memory layout of the Douglas kernel (offsets in bytes from the dynamic smem base)
@@ -61,7 +68,8 @@ struct HadiSmemLayout {
   size_t U, Y, ti, tj, tjp, divk, ring, bars, total;
 };
 HADI_HD HadiSmemLayout hadi_smem_layout(int m1, int m2, int ld, int n1, int n2, int pj, bool ring,
-                                        bool global_state = false, bool coop = false, bool lean = false) {
+                                        bool global_state = false, bool coop = false, bool lean = false,
+                                        bool tmem = false) {
   (void)m1;
   HadiSmemLayout s;
   size_t off = 0;
@@ -78,6 +86,7 @@ HADI_HD HadiSmemLayout hadi_smem_layout(int m1, int m2, int ld, int n1, int n2, 
   s.ring = off;
   if (ring) off += sizeof(double) * (size_t)HADI_NS * HADI_KF * pj;
   if (coop) off += (size_t)hadi_co_stage_bytes(m2);
+  if (tmem) off += sizeof(double) * (size_t)(n1 + 4);   // dummy row of the half sweeps (hadi_tmem_solve_a1)
   s.bars = off;
   if (ring) off += sizeof(unsigned long long) * 2 * HADI_NS;
   s.total = off + 16;

@@ -265,6 +265,687 @@ __device__ __forceinline__ void hadi_fast_solve_a1(const HadiItem& it, const Had
 }
 
 // ----------------------------------------------------------------------------------------------
+// S1 with the back-substitution factors in TENSOR MEMORY (FEED 5).
+//
+// The 256 KB of tensor memory of a Blackwell SM are idle in this kernel (no tcgen05.mma anywhere), and the
+// (pivot, prepared reciprocal) stream of the Thomas back substitution — 2 x (m2+1) x m1 doubles, 83 KB at
+// 101 x 51 — is what phase S1 waits for when it lives in L2 (13 k of the 17 k cycles of S1).
+// A CTA therefore allocates 256 (101 x 51) or 128 (51 x 26) TMEM columns at start-up — two / three CTAs per SM
+// fit — and keeps that stream there for the life of an item: tcgen05.ld returns in a few tens of cycles and
+// touches neither shared memory nor the L2.
+//
+// Layout.  TMEM is addressed as (lane 0..127, column): warp w reaches lanes 32*(w%4) .. +31, each thread its
+// own lane (shape .32x32b).  Chain warp c (rows 13c .. 13c+12, as in the co-operative variant) uses lanes
+// l = 0..12 and l + 16: lane l holds the {pivot, reciprocal} pairs of the FIRST half of row 13c+l's back
+// substitution (nodes i = m1 .. m1/2+1) at columns 4e .. 4e+3, e = 0 .. m1/2-1, lane l + 16 the pairs of the
+// SECOND half (i = m1/2 .. 1) at the same columns.  The sweep runs the same fully unrolled half-row code twice:
+// first lanes 0..15 are live, then x is handed to lane l + 16 by one shuffle and lanes 16..31 are live; the
+// lanes that are not live work on a dummy row of shared memory, so that no store is predicated (a predicated
+// store makes the compiler split the sweep into divergent copies).  Per node the chain lane issues no shuffle
+// and no global load; one tcgen05.ld.x16 per four nodes is requested a chunk ahead.
+__device__ __forceinline__ void hadi_tm_alloc(unsigned* slot_smem, int cols) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(slot_smem);
+  if (cols == 512) asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(a) : "memory");
+  else if (cols == 256) asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(a) : "memory");
+  else asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(a) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void hadi_tm_free(unsigned addr, int cols) {
+  if (cols == 512) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(addr) : "memory");
+  else if (cols == 256) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(addr) : "memory");
+  else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void hadi_tm_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void hadi_tm_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void hadi_tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// one {pivot, reciprocal} pair of this thread's lane
+__device__ __forceinline__ void hadi_tm_st_pair(unsigned taddr, double t, double r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__double2loint(t)),
+               "r"(__double2hiint(t)), "r"(__double2loint(r)), "r"(__double2hiint(r))
+               : "memory");
+}
+// four pairs (16 columns) of this thread's lane; the registers may be read after hadi_tm_wait_ld(q)
+struct HadiTmQuad { unsigned r[16]; };
+__device__ __forceinline__ void hadi_tm_ld_quad(unsigned taddr, HadiTmQuad& q) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(q.r[0]), "=r"(q.r[1]), "=r"(q.r[2]), "=r"(q.r[3]), "=r"(q.r[4]), "=r"(q.r[5]), "=r"(q.r[6]), "=r"(q.r[7]),
+        "=r"(q.r[8]), "=r"(q.r[9]), "=r"(q.r[10]), "=r"(q.r[11]), "=r"(q.r[12]), "=r"(q.r[13]), "=r"(q.r[14]), "=r"(q.r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// the registers are operands of the wait: no use of them can be scheduled above it
+__device__ __forceinline__ void hadi_tm_wait_ld(HadiTmQuad& q) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(q.r[0]), "+r"(q.r[1]), "+r"(q.r[2]), "+r"(q.r[3]), "+r"(q.r[4]), "+r"(q.r[5]), "+r"(q.r[6]), "+r"(q.r[7]),
+                 "+r"(q.r[8]), "+r"(q.r[9]), "+r"(q.r[10]), "+r"(q.r[11]), "+r"(q.r[12]), "+r"(q.r[13]), "+r"(q.r[14]), "+r"(q.r[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ double hadi_tm_piv(const HadiTmQuad& q, int k) { return __hiloint2double((int)q.r[4 * k + 1], (int)q.r[4 * k]); }
+__device__ __forceinline__ double hadi_tm_rcp(const HadiTmQuad& q, int k) { return __hiloint2double((int)q.r[4 * k + 3], (int)q.r[4 * k + 2]); }
+
+HADI_HD constexpr int hadi_tm_half(int m1) { return m1 / 2; }
+// columns a CTA allocates: 4 per node of a half row, rounded up to whole x16 loads, then to a power of two
+HADI_HD constexpr int hadi_tm_cols(int m1) { return (16 * ((hadi_tm_half(m1) + 3) / 4) <= 128) ? 128 : 256; }
+HADI_HD constexpr int hadi_tm_cols_feed(int feed, int m1) { return feed == 6 ? 512 : feed == 7 ? 256 : hadi_tm_cols(m1); }
+
+// Thomas factors of I - theta*dt*A1 (src/hes_a1_kernels.hpp:145-152), chain warps only, all 32 lanes converged.
+// Pass A runs nodes 1 .. m1/2 on every lane; in pass B lanes 0..15 go on with nodes m1/2+1 .. m1 while lanes
+// 16..31 start the recurrence again at node 1, so that in iteration k both groups hold the pair that belongs
+// at columns 4(m1/2 - k) of their own lane and one tcgen05.st serves both.  Multipliers go to fM (global, read
+// by the forward sweep); lanes that own no row shadow row 13c (same values to the same words).
+template <int M1, int M2>
+__device__ __forceinline__ void hadi_tmem_factor(const HadiItem& it, const HadiView& w, const double* vg, int tid,
+                                                 unsigned tmem) {
+  constexpr int NR = HADI_CO_NR, NW = hadi_co_warps(M2), H = hadi_tm_half(M1);
+  constexpr int N1 = hadi_geo_n1(M1), PJ = hadi_geo_pj(M2);
+  static_assert(M1 % 2 == 0 && NW <= 4, "half-row layout needs an even m1 and at most four chain warps");
+  const int warp = tid >> 5, lane = tid & 31;
+  if (warp >= NW) return;
+  const int g = lane >> 4, l = lane & 15;
+  const bool own = (l < NR) && (warp * NR + l <= M2);
+  const int j = warp * NR + (own ? l : 0);
+  const unsigned mine = tmem + ((unsigned)(32 * warp) << 16);
+  const double vj = vg[j];
+  const double* hs2 = w.ti + TI_HS2 * N1;
+  const double* dsm = w.ti + TI_DSM * N1;
+  const double* ds0 = w.ti + TI_DS0 * N1;
+  const double* dsp = w.ti + TI_DSP * N1;
+  const double* sv = w.ti + TI_S * N1;
+  const double* bsm = w.ti + TI_BSM * N1;
+  const double* bs0 = w.ti + TI_BS0 * N1;
+  const double* bbp = w.ti + TI_BBP * N1;
+  const double theta = it.theta, dt = it.dt;
+  const double rdiff = it.r_d - it.r_f;
+  double t = 1.0;           // impl_main(j,0)
+  double iu_prev = 0.0;     // impl_upper(j,0)
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    int i0 = 0;             // this lane handles node i0 + k in iteration k
+    if (pass == 1) {
+      if (g == 0) i0 = H;
+      else { t = 1.0; iu_prev = 0.0; }
+    }
+#pragma unroll 1
+    for (int k = 1; k <= H; ++k) {
+      const int i = i0 + k;
+      double il, im, iu;
+      if (i < M1) {
+        const double a = hs2[i] * vj;
+        const double b = rdiff * sv[i];
+        const double lo = a * dsm[i] + b * bsm[i];
+        const double ma = a * ds0[i] + b * bs0[i] - 0.5 * it.r_d;
+        const double up = a * dsp[i] + bbp[i];
+        il = -theta * dt * lo;
+        im = 1.0 - theta * dt * ma;
+        iu = -theta * dt * up;
+      } else {
+        const double ma = -0.5 * it.r_d;
+        il = 0.0;
+        im = 1.0 - theta * dt * ma;
+        iu = 0.0;
+      }
+      const double m = il / t;
+      t = im - m * iu_prev;
+      iu_prev = iu;
+      w.fM[(size_t)(i - 1) * PJ + j] = m;
+      // node i is element e = M1 - i of the back substitution: e - H*(1-g) = H - k for both groups
+      if (pass == 1) hadi_tm_st_pair(mine + 4u * (unsigned)(H - k), t, hadi_rcp_prep(t));
+    }
+  }
+  hadi_tm_wait_st();
+}
+
+// Phase S1 of the FEED 5 variants.  Forward sweep: multipliers from fM (L2) in chunks of HADI_KF nodes, as in
+// hadi_phase_solve_a1.  Back substitution: two half rows fed from tensor memory (see above).
+// `dummy`: m1 + 2 doubles of shared memory nobody reads.
+template <int M1, int M2, bool EXACT>
+__device__ __forceinline__ void hadi_tmem_solve_a1(const HadiItem& it, const HadiView& w, int tid, unsigned& bad,
+                                                   unsigned tmem, double* dummy, long long* dbg = nullptr) {
+  constexpr int NR = HADI_CO_NR, NW = hadi_co_warps(M2), H = hadi_tm_half(M1), NQ = (H + 3) / 4;
+  constexpr int LD = hadi_geo_ld(M1), N1 = hadi_geo_n1(M1), N2 = hadi_geo_n2(M2), PJ = hadi_geo_pj(M2);
+  constexpr int KF = HADI_KF;
+  const int warp = tid >> 5, lane = tid & 31;
+  if (warp >= NW) return;
+  const int g = lane >> 4, l = lane & 15;
+  const bool own = (l < NR) && (warp * NR + l <= M2);
+  const int j = warp * NR + (own ? l : 0);
+  const unsigned mine = tmem + ((unsigned)(32 * warp) << 16);
+  double* y = w.Y + j * LD;
+  const double vj = w.tj[TJ_V * N2 + j];
+  const double ntd = -it.theta * it.dt;
+#ifdef HADI_PHASE_TIMING
+  const long long dbg_t0 = clock64();
+#endif
+  // first quad of the back substitution: in flight during the whole forward sweep
+  HadiTmQuad qa, qb;
+  hadi_tm_ld_quad(mine, qa);
+  // ---- forward elimination: x_i = y_i - m_i x_{i-1}, i = 1..m1 (both lane groups run the row: same values)
+  double x = y[0];
+  {
+    const double* pm = w.fM + j;
+    constexpr int ncf = (M1 + KF - 1) / KF;
+#pragma unroll
+    for (int cc = 0; cc < ncf; ++cc) {
+      const int ib = cc * KF + 1;
+      double mm[KF], yy[KF];
+#pragma unroll
+      for (int k = 0; k < KF; ++k) {
+        const int i = (ib + k <= M1) ? ib + k : M1;
+        mm[k] = pm[(size_t)(i - 1) * PJ];
+        yy[k] = y[i];
+      }
+#pragma unroll
+      for (int k = 0; k < KF; ++k) {
+        if (ib + k <= M1) {
+          x = yy[k] - mm[k] * x;
+          y[ib + k] = x;
+        }
+      }
+    }
+  }
+#ifdef HADI_PHASE_TIMING
+  if (dbg) dbg[0] += clock64() - dbg_t0;
+#endif
+  // ---- back substitution: x_i = (x_i - impl_upper(j,i) x_{i+1}) / pivot(j,i), i = m1..1
+  // impl_upper(j,i) = -theta*dt*(a*delta_s(+1) + b*beta_s(+1)) from the zero-padded tables (exactly 0 at i = m1)
+  const double* hs2 = w.ti + TI_HS2 * N1;
+  const double* dsp = w.ti + TI_DSP * N1;
+  const double* bbp = w.ti + TI_BBP * N1;
+  constexpr int PB = 2;                                  // shared-memory lookahead of the chain (nodes)
+  double xn = 0.0;
+  unsigned badl = 0;
+  hadi_tm_wait_ld(qa);
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    const int top = M1 - h * H;                          // first (largest) node of this half
+    double* yh = ((g == h) ? y : dummy) + top;           // element e of the half <-> yh[-e]
+    const double* hh = hs2 + top;
+    const double* dh = dsp + top;
+    const double* bh = bbp + top;
+    if (h == 1) {
+      xn = __shfl_sync(0xffffffffu, xn, l);              // lanes 16..31 take the row over from lane l
+      hadi_tm_ld_quad(mine, qa);                         // their first quad (same columns, other lanes' data)
+      hadi_tm_wait_ld(qa);
+    }
+    double yq[PB], hq[PB], dq[PB], bq[PB];
+#pragma unroll
+    for (int e = 0; e < PB; ++e) {
+      yq[e] = yh[-e];
+      hq[e] = hh[-e]; dq[e] = dh[-e]; bq[e] = bh[-e];
+    }
+    double iu = ntd * ((hq[0] * vj) * dq[0] + bq[0]);
+#pragma unroll
+    for (int e = 0; e < H; ++e) {
+      const int f = e + PB;
+      const int c = e / 4, k = e % 4;
+      HadiTmQuad& cur = (c % 2 == 0) ? qa : qb;
+      HadiTmQuad& nxt = (c % 2 == 0) ? qb : qa;
+      if (k == 0 && c + 1 < NQ) hadi_tm_ld_quad(mine + 16u * (unsigned)(c + 1), nxt);   // a chunk ahead of the chain
+      const double tc = hadi_tm_piv(cur, k), rc = hadi_tm_rcp(cur, k), yc = yq[e % PB];
+      double iun = 0.0;
+      if (e + 1 < H) iun = ntd * ((hq[(e + 1) % PB] * vj) * dq[(e + 1) % PB] + bq[(e + 1) % PB]);
+      if (f < H) {
+        yq[e % PB] = yh[-f];
+        hq[e % PB] = hh[-f]; dq[e % PB] = dh[-f]; bq[e % PB] = bh[-f];
+      }
+      x = hadi_div<EXACT>(yc - iu * xn, tc, rc, badl);
+      xn = x;
+      yh[-e] = x;
+      iu = iun;
+      if ((k == 3 || e == H - 1) && c + 1 < NQ) hadi_tm_wait_ld(nxt);
+    }
+    if (g == h && own) bad |= badl;
+    badl = 0;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// S1 entirely out of tensor memory (FEED 6, the "duo" kernel: two solves per CTA, one CTA per SM, all 512 columns).
+//
+// With 512 columns a lane holds 256 doubles: one lane per v-row carries the row's whole back-substitution stream
+// — {pivot, prepared reciprocal} of node i at columns 4(m1-i) .. +3 — and the first HADI_TM_MT Thomas
+// multipliers at columns 4 m1 + 2(i-1).  Two chain warps per solve (rows 0..25 and 26..50 at 101 x 51), as in the
+// plain-load kernel, so the FP64 pipe sees no more instructions than before (an FP64 instruction costs the pipe
+// the same whether 13 or 32 lanes are active; the pair layout of FEED 5 above doubles the chain warps and loses
+// more in the other CTA's phases than S1 gains).  The multipliers that do not fit are re-formed on the way from
+// the pair of the previous node: m_i = impl_lower(j,i) / pivot(j,i-1) with the prepared reciprocal — the bit
+// pattern the factorisation stored (hadi_div) — 7 FP64 operations off the dependent chain.  Phase S1 then touches
+// neither the L2 nor (beyond Y and three coefficient tables) shared memory.
+// Team t of the CTA runs its chains on the two team-local warps whose CTA-wide warp index falls into TMEM quarters
+// 2t and 2t + 1 (`wbase`: warps 0, 1 of team 0; warps 2, 3 of team 1 when a team has 8 warps, 0, 1 when it has 10).
+#ifndef HADI_TM_MT
+#define HADI_TM_MT 56
+#endif
+HADI_HD constexpr int hadi_tm2_rows(int m2) { return (m2 + 2) / 2; }   // v-rows per chain warp
+
+template <int M1, int M2>
+__device__ __forceinline__ void hadi_tmem2_factor(const HadiItem& it, const HadiView& w, const double* vg, int tid,
+                                                  unsigned tmem, int wbase) {
+  constexpr int NRW = hadi_tm2_rows(M2), MT = HADI_TM_MT;
+  constexpr int N1 = hadi_geo_n1(M1);
+  static_assert(NRW <= 32 && 4 * M1 + 2 * MT <= 512, "one TMEM lane per v-row: 4 columns per node + the stored multipliers");
+  const int warp = (tid >> 5) - wbase, lane = tid & 31;   // chain warps: team-local warps wbase, wbase + 1
+  if (warp < 0 || warp >= 2) return;
+  const bool own = (lane < NRW) && (warp * NRW + lane <= M2);
+  const int j = warp * NRW + (own ? lane : 0);
+  const unsigned mine = tmem + ((unsigned)(32 * ((threadIdx.x >> 5) & 3)) << 16);
+  const double vj = vg[j];
+  const double* hs2 = w.ti + TI_HS2 * N1;
+  const double* dsm = w.ti + TI_DSM * N1;
+  const double* ds0 = w.ti + TI_DS0 * N1;
+  const double* dsp = w.ti + TI_DSP * N1;
+  const double* sv = w.ti + TI_S * N1;
+  const double* bsm = w.ti + TI_BSM * N1;
+  const double* bs0 = w.ti + TI_BS0 * N1;
+  const double* bbp = w.ti + TI_BBP * N1;
+  const double theta = it.theta, dt = it.dt;
+  const double rdiff = it.r_d - it.r_f;
+  double t = 1.0;           // impl_main(j,0)
+  double iu_prev = 0.0;     // impl_upper(j,0)
+#pragma unroll 1
+  for (int i = 1; i <= M1; ++i) {
+    double il, im, iu;
+    if (i < M1) {
+      const double a = hs2[i] * vj;
+      const double b = rdiff * sv[i];
+      const double lo = a * dsm[i] + b * bsm[i];
+      const double ma = a * ds0[i] + b * bs0[i] - 0.5 * it.r_d;
+      const double up = a * dsp[i] + bbp[i];
+      il = -theta * dt * lo;
+      im = 1.0 - theta * dt * ma;
+      iu = -theta * dt * up;
+    } else {
+      const double ma = -0.5 * it.r_d;
+      il = 0.0;
+      im = 1.0 - theta * dt * ma;
+      iu = 0.0;
+    }
+    const double m = il / t;
+    t = im - m * iu_prev;
+    iu_prev = iu;
+    hadi_tm_st_pair(mine + 4u * (unsigned)(M1 - i), t, hadi_rcp_prep(t));
+    if (i <= MT) {
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(mine + 4u * (unsigned)M1 + 2u * (unsigned)(i - 1)),
+                   "r"(__double2loint(m)), "r"(__double2hiint(m))
+                   : "memory");
+    }
+  }
+  hadi_tm_wait_st();
+}
+
+// One quad (four nodes, elements 4q .. 4q+3 <-> i = M1-4q .. M1-4q-3) of the back substitution.  `cur` holds the
+// quad's {pivot, reciprocal} pairs, yc / uc its right-hand sides and impl_upper values.  While the dependent chain
+// of the four nodes runs, the operands of the NEXT quad are fetched (tensor memory -> nxt, y and the three
+// coefficient tables -> registers) and its impl_upper values are formed stage by stage, four independent
+// operations after each node of the chain, so that neither a load nor an off-chain FP64 latency lands on the chain.
+template <int M1, bool EXACT, bool MORE>
+__device__ __forceinline__ void hadi_tm2_bwd_quad(const HadiTmQuad& cur, HadiTmQuad& nxt, const double (&yc)[4],
+                                                  const double (&uc)[4], double (&yn)[4], double (&un)[4],
+                                                  double* yq, const double* hq, const double* dq, const double* bq,
+                                                  unsigned next_cols, double vj, double ntd, double& xn,
+                                                  unsigned& badl) {
+  // yq, hq, dq, bq point at the first (largest-i) node of THIS quad: element k is [-k]; the next quad starts at [-4]
+  double hn[4], dn[4], bn[4];
+  if (MORE) {
+    hadi_tm_ld_quad(next_cols, nxt);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      yn[k] = yq[-4 - k];
+      hn[k] = hq[-4 - k]; dn[k] = dq[-4 - k]; bn[k] = bq[-4 - k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double x = hadi_div<EXACT>(yc[k] - uc[k] * xn, hadi_tm_piv(cur, k), hadi_tm_rcp(cur, k), badl);
+    xn = x;
+    yq[-k] = x;
+    if (MORE) {
+      // stage k of the next quad's impl_upper = ntd * ((hs2 * v) * dsp + bbp), all four nodes
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (k == 0) un[q] = hn[q] * vj;
+        if (k == 1) un[q] = un[q] * dn[q];
+        if (k == 2) un[q] = un[q] + bn[q];
+        if (k == 3) un[q] = ntd * un[q];
+      }
+    }
+  }
+  if (MORE) hadi_tm_wait_ld(nxt);
+}
+
+// Forward counterpart for the nodes whose multiplier is re-formed: quad `cur` holds the pairs of elements
+// 4c .. 4c+3, i.e. of nodes i-1 for i = M1-4c+1 .. M1-4c-2 (descending slots 3..0 serve ascending i).
+// m_i = impl_lower(j,i) / pivot(j,i-1), impl_lower = ntd * ((hs2 v) dsm + (rdiff s) bsm): formed for the four
+// nodes stage by stage (nine stages of four independent operations), then the chain x_i = y_i - m_i x_{i-1}.
+template <int M1, bool EXACT>
+__device__ __forceinline__ void hadi_tm2_fwd_quad(const HadiTmQuad& cur, int i0, int nn, int slot0, double* y,
+                                                  const double* hs2, const double* dsm, const double* sv,
+                                                  const double* bsm, double vj, double ntd, double rdiff, double& x,
+                                                  unsigned& badl) {
+  // nodes i0 .. i0+nn-1 (nn <= 4, compile-time after inlining); node i0+k uses slot slot0-k of `cur`
+  double il[4], yy[4], mm[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k < nn) {
+      const int i = i0 + k;
+      yy[k] = y[i];
+      il[k] = hs2[i] * vj;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (k < nn) il[k] = il[k] * dsm[i0 + k];
+  double bb[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (k < nn) bb[k] = rdiff * sv[i0 + k];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (k < nn) bb[k] = bb[k] * bsm[i0 + k];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (k < nn) il[k] = il[k] + bb[k];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (k < nn) il[k] = (i0 + k < M1) ? ntd * il[k] : 0.0;     // impl_lower(j, m1) = 0
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (k < nn) mm[k] = hadi_div<EXACT>(il[k], hadi_tm_piv(cur, slot0 - k), hadi_tm_rcp(cur, slot0 - k), badl);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k < nn) {
+      x = yy[k] - mm[k] * x;
+      y[i0 + k] = x;
+    }
+  }
+}
+
+template <int M1, int M2, bool EXACT>
+__device__ __forceinline__ void hadi_tmem2_solve_a1(const HadiItem& it, const HadiView& w, int tid, unsigned& bad,
+                                                    unsigned tmem, int wbase, long long* dbg = nullptr) {
+  constexpr int NRW = hadi_tm2_rows(M2), MT = HADI_TM_MT;
+  constexpr int LD = hadi_geo_ld(M1), N1 = hadi_geo_n1(M1), N2 = hadi_geo_n2(M2);
+  static_assert(MT % 8 == 0 && MT >= 8 && MT < M1 && M1 % 4 == 0 && (M1 - MT) % 4 == 0,
+                "stored multipliers come in x16 loads of eight, pairs in quads of four");
+  const int warp = (tid >> 5) - wbase, lane = tid & 31;
+  if (warp < 0 || warp >= 2) return;
+  const bool own = (lane < NRW) && (warp * NRW + lane <= M2);
+  const int j = warp * NRW + (own ? lane : 0);
+  const unsigned mine = tmem + ((unsigned)(32 * ((threadIdx.x >> 5) & 3)) << 16);
+  double* y = w.Y + j * LD;
+  const double vj = w.tj[TJ_V * N2 + j];
+  const double ntd = -it.theta * it.dt;
+  const double* hs2 = w.ti + TI_HS2 * N1;
+  const double* dsm = w.ti + TI_DSM * N1;
+  const double* dsp = w.ti + TI_DSP * N1;
+  const double* sv = w.ti + TI_S * N1;
+  const double* bsm = w.ti + TI_BSM * N1;
+  const double* bbp = w.ti + TI_BBP * N1;
+  const double rdiff = it.r_d - it.r_f;
+  unsigned badl = 0;
+#ifdef HADI_PHASE_TIMING
+  const long long dbg_t0 = clock64();
+#endif
+  HadiTmQuad qa, qb;
+  // ---- forward elimination: x_i = y_i - m_i x_{i-1}, i = 1..m1.  The loops are rolled (a few hundred instructions
+  // in all): with tensor memory there is no load to hoist a long way ahead, and the fully unrolled sweeps of the
+  // plain-load kernels are what overflows the instruction cache once two teams run different phases.
+  double x = y[0];
+  {
+    // nodes 1..MT: stored multipliers, eight per load, one load ahead of the chain
+    constexpr int NQ = MT / 8;
+    hadi_tm_ld_quad(mine + 4u * (unsigned)M1, qa);
+    double yc[8], yn[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) yc[k] = y[1 + k];
+    hadi_tm_wait_ld(qa);
+#pragma unroll 1
+    for (int c = 0; c < NQ; ++c) {
+      // next load: the following eight multipliers, or (last round) the first pair quad of the re-formed part
+      const unsigned ncol = (c + 1 < NQ) ? 4u * (unsigned)M1 + 16u * (unsigned)(c + 1) : 16u * (unsigned)((M1 - MT) / 4);
+      hadi_tm_ld_quad(mine + ncol, qb);
+      double* yb = y + 8 * c + 1;
+      if (c + 1 < NQ) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) yn[k] = yb[8 + k];
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const double mc = __hiloint2double((int)qa.r[2 * k + 1], (int)qa.r[2 * k]);
+        x = yc[k] - mc * x;
+        yb[k] = x;
+      }
+      hadi_tm_wait_ld(qb);
+      qa = qb;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) yc[k] = yn[k];
+    }
+    // nodes MT+1..m1, multipliers re-formed from the pair of node i-1 = element M1-i+1: node MT+1 takes slot 0 of
+    // quad C0 = (M1-MT)/4 (in qa now), then quads C0-1 .. 1 serve four nodes each (slots 3..0), quad 0 the last three
+    constexpr int C0 = (M1 - MT) / 4;
+    hadi_tm_ld_quad(mine + 16u * (unsigned)(C0 - 1), qb);
+    hadi_tm2_fwd_quad<M1, EXACT>(qa, MT + 1, 1, 0, y, hs2, dsm, sv, bsm, vj, ntd, rdiff, x, badl);
+    hadi_tm_wait_ld(qb);
+#pragma unroll 1
+    for (int c = C0 - 1; c >= 1; --c) {
+      qa = qb;
+      hadi_tm_ld_quad(mine + 16u * (unsigned)(c - 1), qb);
+      hadi_tm2_fwd_quad<M1, EXACT>(qa, M1 - 4 * c - 2, 4, 3, y, hs2, dsm, sv, bsm, vj, ntd, rdiff, x, badl);
+      hadi_tm_wait_ld(qb);
+    }
+    hadi_tm2_fwd_quad<M1, EXACT>(qb, M1 - 2, 3, 3, y, hs2, dsm, sv, bsm, vj, ntd, rdiff, x, badl);
+  }
+#ifdef HADI_PHASE_TIMING
+  if (dbg) dbg[0] += clock64() - dbg_t0;
+#endif
+  // ---- back substitution: x_i = (x_i - impl_upper(j,i) x_{i+1}) / pivot(j,i), i = m1..1 (element e <-> i = m1 - e)
+  // impl_upper(j,i) = -theta*dt*(a*delta_s(+1) + b*beta_s(+1)) from the zero-padded tables (exactly 0 at i = m1)
+  {
+    constexpr int NQ = M1 / 4;
+    hadi_tm_ld_quad(mine, qa);
+    double ya[4], ua[4], yb[4], ub[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ya[k] = y[M1 - k];
+      ua[k] = ntd * ((hs2[M1 - k] * vj) * dsp[M1 - k] + bbp[M1 - k]);
+    }
+    double xn = 0.0;
+    hadi_tm_wait_ld(qa);
+    int q = 0;
+#pragma unroll 1
+    for (; q + 2 < NQ; q += 2) {
+      const int i0 = M1 - 4 * q;
+      hadi_tm2_bwd_quad<M1, EXACT, true>(qa, qb, ya, ua, yb, ub, y + i0, hs2 + i0, dsp + i0, bbp + i0,
+                                         mine + 16u * (unsigned)(q + 1), vj, ntd, xn, badl);
+      hadi_tm2_bwd_quad<M1, EXACT, true>(qb, qa, yb, ub, ya, ua, y + i0 - 4, hs2 + i0 - 4, dsp + i0 - 4, bbp + i0 - 4,
+                                         mine + 16u * (unsigned)(q + 2), vj, ntd, xn, badl);
+    }
+    // one or two quads are left
+    {
+      const int i0 = M1 - 4 * q;
+      if (q + 2 == NQ) {
+        hadi_tm2_bwd_quad<M1, EXACT, true>(qa, qb, ya, ua, yb, ub, y + i0, hs2 + i0, dsp + i0, bbp + i0,
+                                           mine + 16u * (unsigned)(q + 1), vj, ntd, xn, badl);
+        hadi_tm2_bwd_quad<M1, EXACT, false>(qb, qa, yb, ub, ya, ua, y + i0 - 4, hs2 + i0 - 4, dsp + i0 - 4, bbp + i0 - 4,
+                                            0u, vj, ntd, xn, badl);
+      } else {
+        hadi_tm2_bwd_quad<M1, EXACT, false>(qa, qb, ya, ua, yb, ub, y + i0, hs2 + i0, dsp + i0, bbp + i0, 0u, vj, ntd,
+                                            xn, badl);
+      }
+    }
+  }
+  if (own) bad |= badl;
+}
+
+// ----------------------------------------------------------------------------------------------
+// S1 with the back-substitution stream in tensor memory, two CTAs per SM (FEED 7, "relay").
+//
+// 256 columns per CTA hold 64 {pivot, reciprocal} pairs per lane, and a v-row needs 100.  The sweep is therefore run
+// as a relay: warps 0 and 1 (rows 0..25 / 26..50, one lane per row, as the plain-load kernel assigns them) carry
+// the chain through elements 0..63 out of their own lanes, then warps 2 and 3 — idle in this phase otherwise —
+// take the rows over for elements 64..99, whose pairs sit in THEIR quarters of tensor memory.  The hand-over costs
+// one named barrier per sweep (x of the last node is already where the next node reads it: in Y); every node is
+// still processed by exactly one warp, so the FP64 pipe sees the instruction count of the plain-load kernel while
+// no back-substitution operand comes from L2 any more.  The forward sweep keeps its multipliers in L2 (fM).
+#define HADI_RELAY_SPLIT 64       /* elements served by warps 0, 1; a multiple of 8 */
+template <int M1, int M2>
+__device__ __forceinline__ void hadi_relay_factor(const HadiItem& it, const HadiView& w, const double* vg, int tid,
+                                                  unsigned tmem) {
+  constexpr int NRW = hadi_tm2_rows(M2), SP = HADI_RELAY_SPLIT;
+  constexpr int N1 = hadi_geo_n1(M1), PJ = hadi_geo_pj(M2);
+  static_assert(NRW <= 32 && 4 * SP <= 256 && 4 * (M1 - SP) <= 256 && M1 > SP, "64 pairs per lane and 256 columns");
+  const int warp = tid >> 5, lane = tid & 31;
+  if (warp >= 4) return;
+  // all four warps run the recurrence of their rows (warps 2, 3 repeat rows of warps 0, 1: they are idle in this
+  // phase, and each warp can only store into its own quarter of tensor memory)
+  const int grp = warp & 1, late = warp >> 1;
+  const bool own = (lane < NRW) && (grp * NRW + lane <= M2);
+  const int j = grp * NRW + (own ? lane : 0);
+  const unsigned mine = tmem + ((unsigned)(32 * warp) << 16);
+  const double vj = vg[j];
+  const double* hs2 = w.ti + TI_HS2 * N1;
+  const double* dsm = w.ti + TI_DSM * N1;
+  const double* ds0 = w.ti + TI_DS0 * N1;
+  const double* dsp = w.ti + TI_DSP * N1;
+  const double* sv = w.ti + TI_S * N1;
+  const double* bsm = w.ti + TI_BSM * N1;
+  const double* bs0 = w.ti + TI_BS0 * N1;
+  const double* bbp = w.ti + TI_BBP * N1;
+  const double theta = it.theta, dt = it.dt;
+  const double rdiff = it.r_d - it.r_f;
+  double t = 1.0;           // impl_main(j,0)
+  double iu_prev = 0.0;     // impl_upper(j,0)
+#pragma unroll 1
+  for (int i = 1; i <= M1; ++i) {
+    double il, im, iu;
+    if (i < M1) {
+      const double a = hs2[i] * vj;
+      const double b = rdiff * sv[i];
+      const double lo = a * dsm[i] + b * bsm[i];
+      const double ma = a * ds0[i] + b * bs0[i] - 0.5 * it.r_d;
+      const double up = a * dsp[i] + bbp[i];
+      il = -theta * dt * lo;
+      im = 1.0 - theta * dt * ma;
+      iu = -theta * dt * up;
+    } else {
+      const double ma = -0.5 * it.r_d;
+      il = 0.0;
+      im = 1.0 - theta * dt * ma;
+      iu = 0.0;
+    }
+    const double m = il / t;
+    t = im - m * iu_prev;
+    iu_prev = iu;
+    const int e = M1 - i;                                   // element of the back substitution
+    if (late == 0) w.fM[(size_t)(i - 1) * PJ + j] = m;
+    if ((e >= SP) == (late == 1)) hadi_tm_st_pair(mine + 4u * (unsigned)(late ? e - SP : e), t, hadi_rcp_prep(t));
+  }
+  hadi_tm_wait_st();
+}
+
+// quads [0, NQ) of a stage whose first element is E0 (node M1 - E0), pairs at columns 0.. of this warp's lanes
+template <int M1, bool EXACT, int E0, int NQ>
+__device__ __forceinline__ void hadi_relay_stage(unsigned mine, double* y, const double* hs2, const double* dsp,
+                                                 const double* bbp, double vj, double ntd, double& xn, unsigned& badl) {
+  HadiTmQuad qa, qb;
+  hadi_tm_ld_quad(mine, qa);
+  constexpr int I0 = M1 - E0;
+  double ya[4], ua[4], yb[4], ub[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    ya[k] = y[I0 - k];
+    ua[k] = ntd * ((hs2[I0 - k] * vj) * dsp[I0 - k] + bbp[I0 - k]);
+  }
+  hadi_tm_wait_ld(qa);
+  int q = 0;
+#pragma unroll 1
+  for (; q + 2 < NQ; q += 2) {
+    const int i0 = I0 - 4 * q;
+    hadi_tm2_bwd_quad<M1, EXACT, true>(qa, qb, ya, ua, yb, ub, y + i0, hs2 + i0, dsp + i0, bbp + i0,
+                                       mine + 16u * (unsigned)(q + 1), vj, ntd, xn, badl);
+    hadi_tm2_bwd_quad<M1, EXACT, true>(qb, qa, yb, ub, ya, ua, y + i0 - 4, hs2 + i0 - 4, dsp + i0 - 4, bbp + i0 - 4,
+                                       mine + 16u * (unsigned)(q + 2), vj, ntd, xn, badl);
+  }
+  const int i0 = I0 - 4 * q;
+  if (NQ % 2 == 0) {
+    hadi_tm2_bwd_quad<M1, EXACT, true>(qa, qb, ya, ua, yb, ub, y + i0, hs2 + i0, dsp + i0, bbp + i0,
+                                       mine + 16u * (unsigned)(q + 1), vj, ntd, xn, badl);
+    hadi_tm2_bwd_quad<M1, EXACT, false>(qb, qa, yb, ub, ya, ua, y + i0 - 4, hs2 + i0 - 4, dsp + i0 - 4, bbp + i0 - 4, 0u,
+                                        vj, ntd, xn, badl);
+  } else {
+    hadi_tm2_bwd_quad<M1, EXACT, false>(qa, qb, ya, ua, yb, ub, y + i0, hs2 + i0, dsp + i0, bbp + i0, 0u, vj, ntd, xn,
+                                        badl);
+  }
+}
+
+template <int M1, int M2, bool EXACT>
+__device__ __forceinline__ void hadi_relay_solve_a1(const HadiItem& it, const HadiView& w, int tid, unsigned& bad,
+                                                    unsigned tmem, long long* dbg = nullptr) {
+  constexpr int NRW = hadi_tm2_rows(M2), SP = HADI_RELAY_SPLIT;
+  constexpr int LD = hadi_geo_ld(M1), N1 = hadi_geo_n1(M1), N2 = hadi_geo_n2(M2), PJ = hadi_geo_pj(M2);
+  constexpr int KF = HADI_KF;
+  static_assert(M1 % 4 == 0 && SP % 4 == 0, "quads of four nodes");
+  const int warp = tid >> 5, lane = tid & 31;
+  if (warp >= 4) return;
+  const int grp = warp & 1, late = warp >> 1;
+  const bool own = (lane < NRW) && (grp * NRW + lane <= M2);
+  const int j = grp * NRW + (own ? lane : 0);
+  const unsigned mine = tmem + ((unsigned)(32 * warp) << 16);
+  double* y = w.Y + j * LD;
+  const double vj = w.tj[TJ_V * N2 + j];
+  const double ntd = -it.theta * it.dt;
+  const double* hs2 = w.ti + TI_HS2 * N1;
+  const double* dsp = w.ti + TI_DSP * N1;
+  const double* bbp = w.ti + TI_BBP * N1;
+  unsigned badl = 0;
+  if (late == 0) {
+#ifdef HADI_PHASE_TIMING
+    const long long dbg_t0 = clock64();
+#endif
+    // ---- forward elimination: x_i = y_i - m_i x_{i-1}, i = 1..m1, multipliers from L2 in chunks
+    double x = y[0];
+    {
+      const double* pm = w.fM + j;
+      constexpr int ncf = (M1 + KF - 1) / KF;
+#pragma unroll
+      for (int cc = 0; cc < ncf; ++cc) {
+        const int ib = cc * KF + 1;
+        double mm[KF], yy[KF];
+#pragma unroll
+        for (int k = 0; k < KF; ++k) {
+          const int i = (ib + k <= M1) ? ib + k : M1;
+          mm[k] = pm[(size_t)(i - 1) * PJ];
+          yy[k] = y[i];
+        }
+#pragma unroll
+        for (int k = 0; k < KF; ++k) {
+          if (ib + k <= M1) {
+            x = yy[k] - mm[k] * x;
+            y[ib + k] = x;
+          }
+        }
+      }
+    }
+#ifdef HADI_PHASE_TIMING
+    if (dbg) dbg[0] += clock64() - dbg_t0;
+#endif
+    // ---- back substitution, elements 0 .. SP-1 (nodes m1 .. m1-SP+1)
+    double xn = 0.0;
+    hadi_relay_stage<M1, EXACT, 0, SP / 4>(mine, y, hs2, dsp, bbp, vj, ntd, xn, badl);
+    // hand the rows to warps 2, 3: x of node m1-SP+1 is in Y
+    asm volatile("bar.arrive 1, 128;" ::: "memory");
+  } else {
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    // ---- elements SP .. m1-1 (nodes m1-SP .. 1) out of this warp's own quarter of tensor memory
+    double xn = y[M1 - SP + 1];
+    hadi_relay_stage<M1, EXACT, SP, (M1 - SP) / 4>(mine, y, hs2, dsp, bbp, vj, ntd, xn, badl);
+  }
+  if (own) bad |= badl;
+}
+
+// ----------------------------------------------------------------------------------------------
 // R + S2 fused: (I - theta*dt*A2) U = Y1 + theta*dt*(b2*e1 - (A2 U + b2*e0)), one thread per s-column on the
 // natural layout (stride LD).  Phase R (src/device_solver.hpp:254-260) is point-wise in the column, so the
 // thread that is about to start the dependent forward chain of node j forms that node's right-hand side on

@@ -34,7 +34,9 @@ EXPORTS = [
     "hadi_batch_phase_cycles", "hadi_bs_vega", "hadi_bs_implied_vol", "hadi_bs_implied_vol_bisect",
     "hadi_dividend_adjusted_spot", "hadi_market_prices", "hadi_implied_vols", "hadi_write_calibration_csv",
     "hadi_batch_create_ex", "hadi_batch_values_per_item", "hadi_jacobian_assemble_ex", "hadi_jacobian_v0_weight",
-    "hadi_jacobian_batch_ex", "hadi_calibrate_ex", "hadi_plan_schedule",
+    "hadi_jacobian_batch_ex", "hadi_calibrate_ex", "hadi_plan_schedule", "hadi_exact_reruns",
+    "hadi_batch_exact_reruns", "hadi_nccl_unique_id", "hadi_comm_init", "hadi_comm_finalize", "hadi_comm_world",
+    "hadi_comm_rank", "hadi_price_batch_sharded", "hadi_jacobian_batch_sharded",
 ]
 
 
@@ -61,7 +63,7 @@ class LmOptions(C.Structure):
 class LmResult(C.Structure):
     _fields_ = [("params", C.c_double * 5), ("final_error", C.c_double), ("lambda_", C.c_double),
                 ("delta_norm", C.c_double), ("iterations", C.c_int), ("converged", C.c_int),
-                ("pde_solves", C.c_int), ("gpu_ms", C.c_double)]
+                ("pde_solves", C.c_int), ("gpu_ms", C.c_double), ("exact_reruns", C.c_longlong)]
 
 
 class JacobianOptions(C.Structure):
@@ -108,6 +110,20 @@ def lib():
         L.hadi_version.restype = C.c_char_p
         L.hadi_kernel_launches.argtypes = [C.c_void_p]
         L.hadi_kernel_launches.restype = C.c_longlong
+        L.hadi_nccl_unique_id.argtypes = [C.c_void_p]
+        L.hadi_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.hadi_comm_finalize.argtypes = [C.c_void_p]
+        L.hadi_comm_finalize.restype = None
+        L.hadi_comm_world.argtypes = [C.c_void_p]
+        L.hadi_comm_rank.argtypes = [C.c_void_p]
+        L.hadi_price_batch_sharded.argtypes = [C.c_void_p, C.POINTER(Model), C.POINTER(Numerics), C.c_int,
+                                               C.POINTER(Point), _dp]
+        L.hadi_jacobian_batch_sharded.argtypes = [C.c_void_p, C.POINTER(Model), C.POINTER(Numerics), C.c_int,
+                                                  C.POINTER(Point), C.POINTER(JacobianOptions), _dp, _dp]
+        L.hadi_exact_reruns.argtypes = [C.c_void_p]
+        L.hadi_exact_reruns.restype = C.c_longlong
+        L.hadi_batch_exact_reruns.argtypes = [C.c_void_p]
+        L.hadi_batch_exact_reruns.restype = C.c_longlong
         L.hadi_price_batch.argtypes = [C.c_void_p, C.POINTER(Model), C.POINTER(Numerics), C.c_int,
                                        C.POINTER(Point), _dp, _dp, _dp]
         L.hadi_jacobian_batch.argtypes = [C.c_void_p, C.POINTER(Model), C.POINTER(Numerics), C.c_int,
@@ -169,6 +185,18 @@ def lib():
 
 def _d(a):
     return None if a is None else a.ctypes.data_as(_dp)
+
+
+NCCL_ID_BYTES = 128
+
+
+def nccl_unique_id():
+    """128-byte NCCL id (call on rank 0, hand to every rank, then Context.comm_init)."""
+    buf = C.create_string_buffer(NCCL_ID_BYTES)
+    rc = lib().hadi_nccl_unique_id(buf)
+    if rc != OK:
+        raise HadiError(rc, "hadi_nccl_unique_id failed (libnccl.so.2 not loadable?)")
+    return buf.raw
 
 
 def make_model(S0, V0, r_d, r_f, kappa, eta, sigma, rho):
@@ -401,6 +429,35 @@ class Context:
     def kernel_launches(self):
         return lib().hadi_kernel_launches(self._h)
 
+    # ---- in-library exchange (NCCL communicator owned by the context) ---------------------------------------
+    def comm_init(self, world, rank, id_bytes):
+        buf = C.create_string_buffer(bytes(id_bytes), NCCL_ID_BYTES)
+        self._check(lib().hadi_comm_init(self._h, world, rank, buf))
+
+    def comm_finalize(self):
+        lib().hadi_comm_finalize(self._h)
+
+    @property
+    def comm_world(self):
+        return lib().hadi_comm_world(self._h)
+
+    def price_batch_sharded(self, model, num, pts, n):
+        prices = np.zeros(max(n, 1))
+        self._check(lib().hadi_price_batch_sharded(self._h, C.byref(model), C.byref(num.num), n, pts, _d(prices)))
+        return prices[:n]
+
+    def jacobian_batch_sharded(self, model, num, pts, n, mode=MODE_JACOBIAN, eps=1e-6):
+        jo = make_jacobian_options(mode, eps)
+        J, base = np.zeros((max(n, 1), 5)), np.zeros(max(n, 1))
+        self._check(lib().hadi_jacobian_batch_sharded(self._h, C.byref(model), C.byref(num.num), n, pts, C.byref(jo),
+                                                      _d(J), _d(base)))
+        return J[:n], base[:n]
+
+    @property
+    def exact_reruns(self):
+        """Solves this context repeated with IEEE divisions (guarded division out of range / hand-off time-out)."""
+        return lib().hadi_exact_reruns(self._h)
+
     def transfer_bytes(self):
         a, b = C.c_longlong(0), C.c_longlong(0)
         self._check(lib().hadi_transfer_bytes(self._h, C.byref(a), C.byref(b)))
@@ -452,7 +509,7 @@ class Context:
                                                 None if comm is None else C.byref(comm), C.byref(res)))
         return dict(params=list(res.params), final_error=res.final_error, lam=res.lambda_,
                     delta_norm=res.delta_norm, iterations=res.iterations, converged=res.converged,
-                    pde_solves=res.pde_solves, gpu_ms=res.gpu_ms)
+                    pde_solves=res.pde_solves, gpu_ms=res.gpu_ms, exact_reruns=res.exact_reruns)
 
 
 class Batch:
@@ -476,6 +533,10 @@ class Batch:
         vals = np.zeros(max(nv, 1))
         self.ctx._check(lib().hadi_batch_fetch(self._h, _d(vals)))
         return vals[:nv]
+
+    @property
+    def exact_reruns(self):
+        return lib().hadi_batch_exact_reruns(self._h)
 
     def elapsed_ms(self):
         ms = C.c_float(0.0)

@@ -86,3 +86,19 @@ def make_comm(hadi, rank, world, device=None, dist=None):
     comm = hadi.Comm(rank, world, fn, None)
     comm._keep = (fn, _cb)
     return comm
+
+
+def attach_nccl(hadi, ctx, rank, world, dist=None, device=None):
+    """Give `ctx` its own NCCL communicator (in-library exchange, include/hadi.h: hadi_comm_init): rank 0 creates the
+    id, torch.distributed broadcasts the 128 bytes once, every rank joins.  After this hadi_calibrate(comm=None) and the
+    *_sharded entry points run their all-gathers inside libhadi.so on the context's stream."""
+    import torch
+
+    if dist is None:
+        import torch.distributed as dist
+    t = torch.zeros(hadi.NCCL_ID_BYTES, dtype=torch.uint8, device=device)
+    if rank == 0:
+        t.copy_(torch.frombuffer(bytearray(hadi.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(t, src=0)
+    ctx.comm_init(world, rank, bytes(t.cpu().numpy().tobytes()))
+    return ctx

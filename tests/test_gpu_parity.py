@@ -539,3 +539,130 @@ def test_device_resident_grid_pool(hadi, monkeypatch):
     ref2 = c2.price_batch(mdl, num, pts2, n2)["prices"].copy()
     c2.close()
     assert np.array_equal(a, ref) and np.array_equal(b, ref) and np.array_equal(c, ref2)
+
+
+# ---- round 2: goldens of the reference itself on the 101x51 grid and for every shipped LM driver ------------------
+def test_jacobians_101x51_match_golden(hadi, ctx):
+    """All four entry-point families (European, American, dividends, American + dividends) on the headline grid,
+    with the V0 + eps v-grid of the V0 column (tests/golden/jacobians_101x51.json, from oracle/_ref)."""
+    G = golden("jacobians_101x51.json")
+    for c in G["cases"]:
+        b = dict(G["base"])
+        theta = b.pop("theta")
+        num = hadi.make_numerics(c["m1"], c["m2"], theta, c["style"], 0, 0, G["divs"] if c["div"] else None)
+        pts, n = hadi.make_points(c["strikes"], 1.0, c["N"])
+        J, base = ctx.jacobian_batch(hadi.make_model(**b), num, pts, n, c["eps"])
+        assert [repr(float(x)) for x in base] == c["base"]
+        assert [[repr(float(x)) for x in row] for row in J] == c["J"]
+
+
+def _lm_against(hadi, ctx, G, K, T, N, market, divs=None):
+    num = hadi.make_numerics(G["m1"], G["m2"], 0.8, G["style"], hadi.CALL, hadi.DOUGLAS, divs)
+    pts, n = hadi.make_points(K, T, N)
+    res = ctx.calibrate(hadi.make_model(**BASE), num, pts, n, market, G["max_iter"], G["tol"], G["delta_tol"])
+    assert res["iterations"] == G["iterations"] and res["converged"] == G["converged"]
+    assert [repr(float(x)) for x in res["params"]] == G["params"]
+    assert repr(float(res["final_error"])) == G["final_error"]
+    assert repr(float(res["lam"])) == G["lam"]
+    assert repr(float(res["delta_norm"])) == G["trajectory"][-1]["delta_norm"]
+    assert res["pde_solves"] == G["pde_solves"]
+    return res
+
+
+@pytest.mark.parametrize("name", ["config3_51x26", "config3_101x51"])
+def test_lm_baseline_config3_matches_reference(hadi, ctx, name):
+    """BASELINE configs[2] as stated: LM calibration to the 10-strike x 10-maturity surface on both grids; parameters,
+    error, lambda and step norm repr-equal to the reference's own LM loop (tests/golden/lm_more.json)."""
+    G = golden("lm_more.json")[name]
+    mats = [1.0 + i * 0.25 if i < 8 else 3.0 + (i - 8) * 0.5 for i in range(10)]
+    K, T, N = [], [], []
+    for Tm in mats:
+        for s in range(10):
+            K.append(95.0 + 1.0 * s)
+            T.append(Tm)
+            N.append(max(20, int(Tm * 20)))
+    market = [hadi.bs_call(100.0, k, 0.025, 0.2, t) for k, t in zip(K, T)]
+    _lm_against(hadi, ctx, G, K, T, N, market)
+
+
+def test_lm_shipped_european_driver_clamps(hadi, ctx):
+    """test_calibration_european (src/heston_calibration.cpp:26): 60 strikes, one maturity; the sigma and rho clamps
+    are active in the last two iterations (golden `clamped`)."""
+    G = golden("lm_more.json")["shipped_european"]
+    assert any(s["clamped"] for s in G["trajectory"])
+    K = [100.0 * 0.7 + i * 1 for i in range(60)]
+    market = [hadi.bs_call(100.0, k, 0.025, 0.2, 1.0) for k in K]
+    res = _lm_against(hadi, ctx, G, K, [1.0] * 60, [20] * 60, market)
+    assert res["params"][2] == 0.01 and res["params"][3] == -1.0
+
+
+def test_lm_shipped_american_dividend_driver_rejects(hadi, ctx):
+    """test_calibration_american_divident_multi_maturity (src/heston_calibration.cpp:3245): 3 maturities x 60 strikes,
+    market generated by the model itself at (3.0, 0.1, 0.05, 0.2, 0.06); 18 iterations with rejected steps (lambda
+    raised), 22 500 PDE solves."""
+    G = golden("lm_more.json")["shipped_american_dividend"]
+    assert any(s.get("accepted") is False for s in G["trajectory"])
+    K, T, N = [], [], []
+    for Tm in (1.0, 1.5, 2.0):
+        for i in range(60):
+            K.append(100.0 * 0.7 + i * 1)
+            T.append(Tm)
+            N.append(max(20, int(Tm * 20)))
+    divs = tuple(G["divs"])
+    kap, eta, sig, rho, v0 = G["market_params"]
+    gen = dict(BASE, kappa=kap, eta=eta, sigma=sig, rho=rho, V0=v0)
+    num = hadi.make_numerics(50, 25, 0.8, hadi.AMERICAN, hadi.CALL, hadi.DOUGLAS, divs)
+    pts, n = hadi.make_points(K, T, N)
+    market = ctx.price_batch(hadi.make_model(**gen), num, pts, n)["prices"].copy()
+    assert digest(market) == G["market_sha256"]
+    _lm_against(hadi, ctx, G, K, T, N, market, divs)
+
+
+def test_rerun_counter_is_visible_without_profiling(hadi, monkeypatch):
+    """hadi_exact_reruns: 0 on option data; when every fast pass is declared out of range (test hook) every solve of
+    the batch is counted, through the one-call entry point and through a prepared batch."""
+    c = hadi.Context(0)
+    mdl = hadi.make_model(**BASE)
+    num = hadi.make_numerics(100, 50, 0.8, hadi.AMERICAN, hadi.CALL, hadi.DOUGLAS, DIVS)
+    pts, n = hadi.make_points([90.0 + k for k in range(40)], 1.0, 8)
+    a = c.price_batch(mdl, num, pts, n)["prices"].copy()
+    assert c.exact_reruns == 0
+    monkeypatch.setenv("HADI_DEBUG_STOP", "-7:0")
+    b = c.price_batch(mdl, num, pts, n)["prices"].copy()
+    assert c.exact_reruns == n
+    bt = c.batch(mdl, num, pts, n)
+    bt.launch()
+    v = bt.fetch().copy()
+    assert bt.exact_reruns == n and c.exact_reruns == 2 * n
+    bt.destroy()
+    monkeypatch.delenv("HADI_DEBUG_STOP")
+    assert np.array_equal(a, b) and np.array_equal(a, v)
+    c.close()
+
+
+def test_duo_kernel_equals_one_solve_per_cta_kernels(hadi, ctx, oracle, monkeypatch):
+    """Variant 8 (two solves per CTA, phase S1 out of tensor memory) against the plain-load variant 0 and the oracle:
+    batches of 1, 2, 149 and 700 solves (idle second team, odd number of work slots, split schedule), all four
+    reference functions, with and without turn-taking between the teams."""
+    mdl = hadi.make_model(**BASE)
+    for style, dv in ((0, None), (1, None), (0, DIVS), (1, DIVS)):
+        num = hadi.make_numerics(100, 50, 0.8, style, hadi.CALL, hadi.DOUGLAS, dv)
+        for n in (1, 2, 149, 700):
+            strikes = [72.0 + 60.0 * k / n for k in range(n)]
+            Ns = [6 + (k % 3) for k in range(n)]
+            pts, _ = hadi.make_points(strikes, 1.0, Ns)
+            monkeypatch.delenv("HADI_NO_DUO", raising=False)
+            monkeypatch.setenv("HADI_FLAGS", "1")
+            duo = ctx.price_batch(mdl, num, pts, n, want_U=(n <= 2), want_lambda=(n <= 2))
+            monkeypatch.setenv("HADI_FLAGS", "0")
+            duo0 = ctx.price_batch(mdl, num, pts, n)
+            monkeypatch.delenv("HADI_FLAGS")
+            monkeypatch.setenv("HADI_NO_DUO", "1")
+            one = ctx.price_batch(mdl, num, pts, n, want_U=(n <= 2), want_lambda=(n <= 2))
+            monkeypatch.delenv("HADI_NO_DUO")
+            assert np.array_equal(duo["prices"], one["prices"]) and np.array_equal(duo0["prices"], one["prices"])
+            if n <= 2:
+                assert np.array_equal(duo["U"], one["U"]) and np.array_equal(duo["lambda"], one["lambda"])
+            o = oracle.solve(strikes[n // 2], Ns[n // 2], 1.0 / Ns[n // 2], m1=100, m2=50, theta=0.8, style=style,
+                             divs=dv, payoff_put=0, want_U=False, want_lambda=False, **BASE)
+            assert duo["prices"][n // 2] == o["price"]
