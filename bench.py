@@ -107,6 +107,21 @@ class ClockSampler(threading.Thread):
 _REF = None
 
 
+class quiet_stdout:
+    """The reference's host schemes print timings to stdout; bench.py must print exactly one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        self._null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self._null, 1)
+
+    def __exit__(self, *a):
+        os.dup2(self._saved, 1)
+        os.close(self._null)
+        os.close(self._saved)
+
+
 def ref_lib():
     """oracle/_ref (the reference's own sources) with its league loop on ALL host cores.  torchrun exports
     OMP_NUM_THREADS=1 to its children, so the thread count is set through the library, not the environment,
@@ -138,7 +153,8 @@ def cpu_baseline(sample_factor=None):
         kind = "reference"
 
         def run():
-            p = R.solve_batch(strikes, NSTEP, 1.0 / NSTEP, m1=M1, m2=M2, theta=THETA, style=1, divs=DIVS, **BASE)["prices"]
+            with quiet_stdout():
+                p = R.solve_batch(strikes, NSTEP, 1.0 / NSTEP, m1=M1, m2=M2, theta=THETA, style=1, divs=DIVS, **BASE)["prices"]
             return p, R.last_compute_seconds()
     else:
         O = OracleLib()
@@ -179,8 +195,9 @@ def run_reference(args):
             times.append(base["value"])
     v = statistics.mean(times) if times else base["value"]
     base["value"] = v
+    ms_per_step = NOPT / v * 1e3
     line = {"metric": METRIC, "value": v, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
             "config": bench_config(),
             "reference_note": "each step = the whole 500-option workload on the host cores (reference entry point timed)",
@@ -191,7 +208,7 @@ def run_reference(args):
     return 0
 
 
-def lm_calibration(hadi, ctx, comm=None, world=1, rank=0, dist=None):
+def lm_calibration(hadi, ctx, solo=None, world=1, rank=0, dist=None):
     """BASELINE configs[2]: LM calibration to a 10-strike x 10-maturity synthetic European surface."""
     K, T, N = c3_surface()
     market = [hadi.bs_call(100.0, k, 0.025, 0.2, t) for k, t in zip(K, T)]
@@ -203,9 +220,15 @@ def lm_calibration(hadi, ctx, comm=None, world=1, rank=0, dist=None):
         for rep in range(3):
             t0 = time.perf_counter()
             res = ctx.calibrate(hadi.make_model(**BASE), num, pts, n, market, 15, 0.1 * math.sqrt(n),
-                                0.1 * (1.0 + math.log(n)), comm=comm)
+                                0.1 * (1.0 + math.log(n)))   # sharded over the context's communicator when one is attached
             ms = (time.perf_counter() - t0) * 1e3
             best = ms if best is None else min(best, ms)
+        if dist is not None:
+            import torch
+
+            tb = torch.tensor([best], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+            best = float(tb[0])
         out[name] = {"wall_ms": round(best, 3), "gpu_ms": round(res["gpu_ms"], 3), "iterations": res["iterations"],
                      "pde_solves": res["pde_solves"], "converged": res["converged"],
                      "params": [repr(float(x)) for x in res["params"]], "final_error": repr(float(res["final_error"]))}
@@ -215,8 +238,8 @@ def lm_calibration(hadi, ctx, comm=None, world=1, rank=0, dist=None):
                 one = None
                 for rep in range(3):
                     t0 = time.perf_counter()
-                    r1 = ctx.calibrate(hadi.make_model(**BASE), num, pts, n, market, 15, 0.1 * math.sqrt(n),
-                                       0.1 * (1.0 + math.log(n)), comm=None)
+                    r1 = solo.calibrate(hadi.make_model(**BASE), num, pts, n, market, 15, 0.1 * math.sqrt(n),
+                                        0.1 * (1.0 + math.log(n)))
                     ms = (time.perf_counter() - t0) * 1e3
                     one = ms if one is None else min(one, ms)
                 out[name]["single_gpu_wall_ms"] = round(one, 3)
@@ -237,7 +260,7 @@ def lm_calibration(hadi, ctx, comm=None, world=1, rank=0, dist=None):
     for rep in range(3):
         t0 = time.perf_counter()
         res = ctx.calibrate(hadi.make_model(**BASE), num, pts, n, market, 15, 0.1 * math.sqrt(n),
-                            0.1 * (1.0 + math.log(n)), comm=comm, jac_mode=hadi.MODE_JACOBIAN_INTERP)
+                            0.1 * (1.0 + math.log(n)), jac_mode=hadi.MODE_JACOBIAN_INTERP)
         ms = (time.perf_counter() - t0) * 1e3
         best = ms if best is None else min(best, ms)
     out["51x26_interpolated_v0_optin"] = {"wall_ms": round(best, 3), "gpu_ms": round(res["gpu_ms"], 3),
@@ -275,20 +298,16 @@ def _digest(a):
     return hashlib.sha256((np.ascontiguousarray(a, dtype=np.float64) + 0.0).tobytes()).hexdigest()[:16]
 
 
-def sharded_chains(hadi, ctx, torch, dev, rank, world, dist):
-    """Strong scaling, one workload split over all ranks (items block-partitioned by cost, hadi_partition; every
-    rank solves its slice; values all-gathered): (a) the 500 American+dividend options of config 2 (the "500
-    options in <= 2 ms on 8 GPUs" target), (b) the SURVEY C5 chain (10 000 European options, mixed maturities),
-    (c) the finite-difference Jacobian of the C3 surface (100 points x 6 solves, 101x51).  Wall time from the barrier
-    before the launches to the gathered values on the host, max over ranks, best of 5; `digest` is a sha256 prefix of
-    the gathered values — it must not change with the number of ranks."""
-    import importlib.util
+def sharded_chains(hadi, ctx, solo, torch, dev, rank, world, dist):
+    """Strong scaling, one workload split over all ranks through the library's own exchange (hadi_*_sharded: items
+    block-partitioned by cost, every rank's kernel publishes into the gather buffer, one ncclAllGather on the context's
+    stream, one D2H): (a) the 500 American+dividend options of config 2 (the "500 options in <= 2 ms on 8 GPUs"
+    target), (b) the SURVEY C5 chain (10 000 European options, mixed maturities), (c) the finite-difference Jacobian of
+    the C3 surface (100 points x 6 solves, 101x51).  Wall time of the one-call entry point (host buffers in, host
+    buffers out, descriptor build and H2D included), from a barrier to the results on the host, max over ranks, best of
+    5; `digest` is a sha256 prefix of the results — it must not change with the number of ranks."""
     import numpy as np
-    import __graft_entry__ as ge
 
-    spec = importlib.util.spec_from_file_location("hadi_dist", os.path.join(ge.PKG, "hadi_dist.py"))
-    hd = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(hd)
     mdl = hadi.make_model(**BASE)
     out = {}
     K5, T5, N5 = c5_chain()
@@ -297,48 +316,40 @@ def sharded_chains(hadi, ctx, torch, dev, rank, world, dist):
               hadi.make_points([70.0 + 0.12 * i for i in range(NOPT)], 1.0, NSTEP), hadi.MODE_PRICE),
              ("c5_chain_10k_sharded", hadi.make_numerics(M1, M2, THETA), hadi.make_points(K5, T5, N5), hadi.MODE_PRICE),
              ("c3_jacobian_600_sharded", hadi.make_numerics(M1, M2, THETA), hadi.make_points(K3, T3, N3), hadi.MODE_JACOBIAN))
+
+    def run(c, num, pts, n, mode, sharded):
+        if mode == hadi.MODE_PRICE:
+            return c.price_batch_sharded(mdl, num, pts, n) if sharded else c.price_batch(mdl, num, pts, n)["prices"]
+        J, b = c.jacobian_batch_sharded(mdl, num, pts, n) if sharded else c.jacobian_batch(mdl, num, pts, n)
+        return np.concatenate([J.ravel(), b])
+
     for name, num, (pts, n), mode in cases:
-        costs = hadi.item_costs(num, pts, n, mode)
-        sl = hd.slices(hadi, costs, world)
-        b, e = sl[rank]
-        bt = ctx.batch(mdl, num, pts, n, mode=mode, begin=b, end=e) if e > b else None
-        counts = [x[1] - x[0] for x in sl]
+        items = n * hadi.ITEMS_PER_OPTION[mode]
         best = None
         for rep in range(7):
             if dist is not None:
                 dist.barrier()
             torch.cuda.synchronize(dev)
             t0 = time.perf_counter()
-            mine = np.zeros(0)
-            if bt is not None:
-                bt.launch()
-                mine = bt.fetch()
-            vals = mine if world == 1 else hd.allgather_values(mine, counts, dist=dist, device=dev)
+            vals = run(ctx, num, pts, n, mode, world > 1)
             ms = (time.perf_counter() - t0) * 1e3
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             if dist is not None:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             if rep >= 2:
                 best = float(t[0]) if best is None else min(best, float(t[0]))
-        out[name] = {"items": int(len(costs)), "wall_ms": round(best, 3),
-                     "solves_per_s": round(len(costs) / (best * 1e-3), 1),
+        out[name] = {"items": int(items), "wall_ms": round(best, 3), "solves_per_s": round(items / (best * 1e-3), 1),
                      "checksum": float(np.sum(vals)), "digest": _digest(vals)}
-        if bt is not None:
-            bt.destroy()
         if world > 1:
             # the same workload on ONE GPU in the same run (rank 0, the others wait): strong-scaling efficiency
-            one = None
             if rank == 0:
-                b1 = ctx.batch(mdl, num, pts, n, mode=mode)
+                one = None
                 for rep in range(5):
-                    torch.cuda.synchronize(dev)
                     t0 = time.perf_counter()
-                    b1.launch()
-                    v1 = b1.fetch()
+                    v1 = run(solo, num, pts, n, mode, False)
                     ms = (time.perf_counter() - t0) * 1e3
                     if rep >= 2:
                         one = ms if one is None else min(one, ms)
-                b1.destroy()
                 out[name]["single_gpu_ms"] = round(one, 3)
                 out[name]["strong_scaling_efficiency"] = round(one / (world * best), 4)
                 out[name]["equals_single_gpu"] = bool(np.array_equal(v1, vals))
@@ -359,8 +370,9 @@ def c5_cpu_baseline():
     idx = list(range(0, 10000, 50))
     Ks, Ts = np.array([K[i] for i in idx]), np.array([T[i] for i in idx])
     Ns = np.array([N[i] for i in idx], dtype=np.int32)
-    R.solve_batch(Ks[:cores], Ns[:cores], Ts[:cores] / Ns[:cores], maturities=Ts[:cores], m1=M1, m2=M2, theta=THETA, multi=1, **BASE)
-    p = R.solve_batch(Ks, Ns, Ts / Ns, maturities=Ts, m1=M1, m2=M2, theta=THETA, multi=1, **BASE)["prices"]
+    with quiet_stdout():
+        R.solve_batch(Ks[:cores], Ns[:cores], Ts[:cores] / Ns[:cores], maturities=Ts[:cores], m1=M1, m2=M2, theta=THETA, multi=1, **BASE)
+        p = R.solve_batch(Ks, Ns, Ts / Ns, maturities=Ts, m1=M1, m2=M2, theta=THETA, multi=1, **BASE)["prices"]
     dt = R.last_compute_seconds()
     return {"value": len(idx) / dt, "unit": "solves/s", "cores": cores, "kind": "reference",
             "sample": "every 50th option of the chain (200 options), %.2f s in the reference entry point" % dt}, p, idx
@@ -399,7 +411,8 @@ def config4_block(hadi, ctx, peaks, with_cpu):
         if ref is not None:
             R = ref[0]
             t0 = time.perf_counter()
-            pr = R.host_scheme(1, K=100.0, T=1.0, m1=m1, m2=m2, N=N, theta=THETA, **BASE)
+            with quiet_stdout():
+                pr = R.host_scheme(1, K=100.0, T=1.0, m1=m1, m2=m2, N=N, theta=THETA, **BASE)
             dt = time.perf_counter() - t0
             out["cpu_baseline"] = {"value": 1.0 / dt, "unit": "solves/s", "cores": 1, "kind": "reference",
                                    "sample": "1 solve through the reference's CS_scheme_shuffled (host matrix classes, serial), %.2f s" % dt,
@@ -517,17 +530,19 @@ def main():
     value = world * NOPT * args.steps / (total_ms_max * 1e-3)
     e2e_value = world * NOPT * args.steps / (e2e_ms_max * 1e-3)
 
-    # ---- LM calibration (configs[2]); sharded over the ranks when world > 1 -------------------------
-    comm = None
+    # ---- LM calibration (configs[2]) and strong-scaling workloads; sharded over the ranks when world > 1 through the
+    # library's own NCCL communicator (hadi_comm_init): no Python in the exchange
+    solo = None
     if dist is not None:
         import importlib.util
 
         spec = importlib.util.spec_from_file_location("hadi_dist", os.path.join(ge.PKG, "hadi_dist.py"))
         hd = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(hd)
-        comm = hd.make_comm(hadi, rank, world, device=dev, dist=dist)
-    lm = lm_calibration(hadi, ctx, comm, world, rank, dist)
-    sharded = sharded_chains(hadi, ctx, torch, dev, rank, world, dist)
+        hd.attach_nccl(hadi, ctx, rank, world, dist=dist, device=dev)
+        solo = hadi.Context(local_rank)     # no communicator: the single-GPU reference of the same run
+    lm = lm_calibration(hadi, ctx, solo, world, rank, dist)
+    sharded = sharded_chains(hadi, ctx, solo, torch, dev, rank, world, dist)
     if dist is not None:
         dist.barrier()
     peaks = {}

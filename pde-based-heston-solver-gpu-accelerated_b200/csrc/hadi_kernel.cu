@@ -483,17 +483,26 @@ __global__ void __launch_bounds__(NT * DUO, MINB) hadi_douglas_kernel(const Hadi
     feed.m1 = m1;
     feed.j = 0;
   }
-  if constexpr (FEED == 5) {
-    // tensor memory: 256 (101 x 51) / 128 (51 x 26) columns per CTA, held until the CTA exits
-    static_assert(M1 > 0, "the tensor-memory feed exists for the grid-specialised variants only");
+  if constexpr (FEED == 5 || FEED == 6 || FEED == 7) {
+    // tensor memory: 256 (101 x 51) / 128 (51 x 26) columns per CTA — all 512 in the duo kernel —, held until
+    // the CTA exits
+    static_assert(M1 > 0, "the tensor-memory feeds exist for the grid-specialised variants only");
+    static_assert(FEED != 6 || (DUO == 2 && MINB == 1), "FEED 6 needs every column of the SM: one CTA, two teams");
     __shared__ unsigned s_tmem;
-    if (tid < 32) hadi_tm_alloc(&s_tmem, hadi_tm_cols(M1));
+    if (threadIdx.x < 32) hadi_tm_alloc(&s_tmem, hadi_tm_cols_feed(FEED, M1));
     hadi_tm_fence_before();
-    HADI_SYNC();
+    __syncthreads();
     hadi_tm_fence_after();
     feed.tmem = s_tmem;
-    feed.dummy = reinterpret_cast<double*>(sbase + lay.ring);
-    for (int k = tid; k < m1 + 2; k += NT) feed.dummy[k] = 0.0;
+    if constexpr (FEED == 6) {
+      // the team's chain warps are the two whose CTA-wide warp index lies in tensor-memory quarters 2 team, 2 team + 1
+      static_assert(NT % 32 == 0, "teams are whole warps");
+      feed.wbase = ((2 * team - team * (NT / 32)) % 4 + 4) % 4;
+    }
+    if constexpr (FEED == 5) {
+      feed.dummy = reinterpret_cast<double*>(sbase + lay.ring);
+      for (int k = tid; k < m1 + 2; k += NT) feed.dummy[k] = 0.0;
+    }
   }
   if constexpr (FEED == 1) {
     feed.m1 = m1;
@@ -640,10 +649,10 @@ __global__ void __launch_bounds__(NT * DUO, MINB) hadi_douglas_kernel(const Hadi
     HADI_SYNC();  // everyone is done with s_item, U and the tables before the next item
     HADI_TICK(6)
   }
-  if constexpr (FEED == 5) {
+  if constexpr (FEED == 5 || FEED == 6 || FEED == 7) {
     hadi_tm_fence_before();
-    HADI_SYNC();
-    if (tid < 32) hadi_tm_free(feed.tmem, hadi_tm_cols(M1));
+    __syncthreads();
+    if (threadIdx.x < 32) hadi_tm_free(feed.tmem, hadi_tm_cols_feed(FEED, M1));
   }
 #ifdef HADI_PHASE_TIMING
   if constexpr (FEED == 1) tacc[6] = feed.wait_cycles;   // slot 6 reports the ring wait of solver thread 0
@@ -809,7 +818,7 @@ __global__ void __cluster_dims__(HADI_CLUSTER, 1, 1) __launch_bounds__(NT, 1) ha
 // config 2) beat the TMA ring (2.78 ms: mbarrier try_wait costs ~90 cycles per chunk on the dependent chain),
 // per-thread cp.async stages (2.97 ms) and L1 prefetches (2.87 ms); at 51x26 the L1 prefetch wins.
 #ifndef HADI_FEED0
-#define HADI_FEED0 0
+#define HADI_FEED0 7   /* 101 x 51: back-substitution stream in tensor memory, relayed between warp pairs */
 #endif
 #ifndef HADI_FEED1
 #define HADI_FEED1 3
@@ -818,7 +827,13 @@ __global__ void __cluster_dims__(HADI_CLUSTER, 1, 1) __launch_bounds__(NT, 1) ha
 #define HADI_DUO_NT 320   /* threads per team of the duo kernel (2 x 256 threads with 128 registers each measured slower) */
 #endif
 #ifndef HADI_DUO
-#define HADI_DUO 1   /* 0: variant 8 (two solves per CTA, S1 out of tensor memory) is never chosen by the planner */
+#define HADI_DUO 0   /* 1: also build variant 8 (two solves per CTA, all of S1 out of tensor memory) and let the planner
+                        prefer it; measured slower than variant 0 with the relay feed */
+#endif
+#if HADI_DUO
+#define HADI_DUO_VARIANT(X) X(8, HADI_DUO_NT, 1, 100, 50, 6, false, 2)
+#else
+#define HADI_DUO_VARIANT(X)
 #endif
 // X(id, threads per team, min CTAs/SM, m1, m2, feed, global state, teams per CTA)
 #define HADI_VARIANTS(X)                    \
@@ -829,7 +844,7 @@ __global__ void __cluster_dims__(HADI_CLUSTER, 1, 1) __launch_bounds__(NT, 1) ha
   X(4, 320, 2, 100, 50, 4, false, 1)       \
   X(5, 512, 1, 0, 0, 1, true, 1)           \
   X(6, 1024, 1, 0, 0, 1, true, 1)          \
-  X(8, HADI_DUO_NT, 1, 100, 50, 6, false, 2)
+  HADI_DUO_VARIANT(X)
 
 struct VariantInfo {
   int id;
@@ -847,7 +862,7 @@ const VariantInfo* variants() {
   };
   return v;
 }
-constexpr int kNumVariants = 8;      // entries of the table above
+constexpr int kNumVariants = 7 + HADI_DUO;   // entries of the table above
 constexpr int kClusterVariant = 7;   // hadi_cluster_kernel: one solve per thread-block cluster
 constexpr int kDuoVariant = 8;
 const VariantInfo* variant_by_id(int id) {

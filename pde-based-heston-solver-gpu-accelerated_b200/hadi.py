@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhadi.so")
+# development aid: HADI_LIB=<file name in this directory> loads an experiment build (csrc/Makefile: make exp)
+LIB_PATH = os.path.join(_HERE, os.environ.get("HADI_LIB", "libhadi.so"))
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)

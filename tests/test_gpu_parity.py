@@ -640,29 +640,25 @@ def test_rerun_counter_is_visible_without_profiling(hadi, monkeypatch):
     c.close()
 
 
-def test_duo_kernel_equals_one_solve_per_cta_kernels(hadi, ctx, oracle, monkeypatch):
-    """Variant 8 (two solves per CTA, phase S1 out of tensor memory) against the plain-load variant 0 and the oracle:
-    batches of 1, 2, 149 and 700 solves (idle second team, odd number of work slots, split schedule), all four
-    reference functions, with and without turn-taking between the teams."""
+def test_tensor_memory_relay_kernel_equals_plain_load_kernel(hadi, ctx, oracle, monkeypatch):
+    """Variant 0 (101x51: back-substitution factors of phase S1 in tensor memory, relayed between warp pairs) against
+    the run-time-dimension variant 2 (plain loads from L2, generic phases) and the oracle: batches of 1, 2, 149, 297
+    and 700 solves (one CTA, odd counts, split schedule), all four reference functions."""
     mdl = hadi.make_model(**BASE)
     for style, dv in ((0, None), (1, None), (0, DIVS), (1, DIVS)):
         num = hadi.make_numerics(100, 50, 0.8, style, hadi.CALL, hadi.DOUGLAS, dv)
-        for n in (1, 2, 149, 700):
+        for n in (1, 2, 149, 297, 700):
             strikes = [72.0 + 60.0 * k / n for k in range(n)]
             Ns = [6 + (k % 3) for k in range(n)]
             pts, _ = hadi.make_points(strikes, 1.0, Ns)
-            monkeypatch.delenv("HADI_NO_DUO", raising=False)
-            monkeypatch.setenv("HADI_FLAGS", "1")
-            duo = ctx.price_batch(mdl, num, pts, n, want_U=(n <= 2), want_lambda=(n <= 2))
-            monkeypatch.setenv("HADI_FLAGS", "0")
-            duo0 = ctx.price_batch(mdl, num, pts, n)
-            monkeypatch.delenv("HADI_FLAGS")
-            monkeypatch.setenv("HADI_NO_DUO", "1")
-            one = ctx.price_batch(mdl, num, pts, n, want_U=(n <= 2), want_lambda=(n <= 2))
-            monkeypatch.delenv("HADI_NO_DUO")
-            assert np.array_equal(duo["prices"], one["prices"]) and np.array_equal(duo0["prices"], one["prices"])
+            monkeypatch.delenv("HADI_FORCE_VARIANT", raising=False)
+            tm = ctx.price_batch(mdl, num, pts, n, want_U=(n <= 2), want_lambda=(n <= 2))
+            monkeypatch.setenv("HADI_FORCE_VARIANT", "2")
+            pl = ctx.price_batch(mdl, num, pts, n, want_U=(n <= 2), want_lambda=(n <= 2))
+            monkeypatch.delenv("HADI_FORCE_VARIANT")
+            assert np.array_equal(tm["prices"], pl["prices"])
             if n <= 2:
-                assert np.array_equal(duo["U"], one["U"]) and np.array_equal(duo["lambda"], one["lambda"])
+                assert np.array_equal(tm["U"], pl["U"]) and np.array_equal(tm["lambda"], pl["lambda"])
             o = oracle.solve(strikes[n // 2], Ns[n // 2], 1.0 / Ns[n // 2], m1=100, m2=50, theta=0.8, style=style,
                              divs=dv, payoff_put=0, want_U=False, want_lambda=False, **BASE)
-            assert duo["prices"][n // 2] == o["price"]
+            assert tm["prices"][n // 2] == o["price"]
