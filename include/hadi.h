@@ -172,6 +172,10 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
 int hadi_batch_num_items(const hadi_batch* b);
 /* values each item publishes: 1, or 3 in HADI_MODE_JACOBIAN_INTERP */
 int hadi_batch_values_per_item(const hadi_batch* b);
+/* Re-aim a prepared batch at new Heston parameters (kappa, eta, sigma, rho, V0 of `model`; S0, r_d, r_f must be those
+ * of creation) without rebuilding it: only the item descriptors and the v-grids are rewritten and uploaded.  The LM
+ * driver uses it for the solver calls of one calibration; the previous launch must have been fetched. */
+int hadi_batch_update_model(hadi_batch* b, const hadi_model* model);
 /* enqueue the solve on the context's stream (asynchronous) */
 int hadi_batch_launch(hadi_batch* b);
 /* device pointer to the item values (one double per item of the slice, slice order) */

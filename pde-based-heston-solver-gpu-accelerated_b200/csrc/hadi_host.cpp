@@ -83,6 +83,14 @@ struct hadi_batch {
   std::vector<int> bufs;  // indices into ctx->pool owned by this batch
   double* h_values = nullptr;  // pinned; one extra word past the values carries the re-solve counter
   long long reruns = 0;        // items of the last fetched launch that were re-solved with IEEE divisions
+  // what hadi_batch_update_model needs: the descriptors as uploaded (sorted), the staging block and its layout
+  std::vector<HadiItem> h_items;
+  int mode = 0, item_begin = 0;
+  double eps5[5] = {0, 0, 0, 0, 0};
+  hadi_model model0{};
+  char* h_stage = nullptr;
+  char* d_stage = nullptr;
+  size_t o_items = 0, o_v = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool launched = false;
 };
@@ -831,8 +839,17 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
     return at;
   };
   const size_t o_items = put(items.data(), sizeof(HadiItem) * (size_t)n_items);
+  b->h_items = items;
+  b->mode = mode;
+  b->item_begin = item_begin;
+  for (int c = 0; c < 5; ++c) b->eps5[c] = eps5[c];
+  b->model0 = *model;
+  b->h_stage = h_stage;
+  b->d_stage = d_stage;
+  b->o_items = o_items;
   const size_t o_s = put(s_pool.data(), sizeof(double) * s_pool.size());
   const size_t o_v = put(v_pool.data(), bytes_v);
+  b->o_v = o_v;
   const size_t o_e = put(e_pool.data(), sizeof(double) * e_pool.size());
   std::vector<double> dv((size_t)std::max(3 * nd, 1), 0.0);
   for (int k = 0; k < nd; ++k) {
@@ -919,6 +936,59 @@ int hadi_batch_num_items(const hadi_batch* b) { return b ? b->n_items : 0; }
 long long hadi_batch_exact_reruns(const hadi_batch* b) { return b ? b->reruns : 0; }
 int hadi_batch_values_per_item(const hadi_batch* b) { return b ? b->stride : 0; }
 double* hadi_batch_values_dev(hadi_batch* b) { return b ? b->L.out_values : nullptr; }
+
+// Re-aim a prepared batch at new Heston parameters (kappa, eta, sigma, rho, V0) without rebuilding it: the LM loop
+// solves the same options dozens of times, and strikes, step tables, schedule and buffers do not depend on the
+// parameters.  Rewrites the parameter fields of the item descriptors and the (up to three) v-grids and uploads those
+// two ranges; S0, r_d, r_f must be the ones the batch was created with.  The previous launch must have been fetched.
+int hadi_batch_update_model(hadi_batch* b, const hadi_model* model) {
+  if (!b || !model) return HADI_ERR_ARG;
+  hadi_ctx* ctx = b->ctx;
+  if (bits(model->S0) != bits(b->model0.S0) || bits(model->r_d) != bits(b->model0.r_d) || bits(model->r_f) != bits(b->model0.r_f))
+    return fail(ctx, HADI_ERR_ARG, "hadi_batch_update_model: S0, r_d and r_f are fixed at creation");
+  cudaSetDevice(ctx->device);
+  const int m2 = b->m2, nc = n_columns(b->mode);
+  std::vector<double> v_pool((size_t)3 * (m2 + 1));
+  v_grid(ctx, m2, model->V0, v_pool.data());
+  const double V0p = model->V0 + b->eps5[4], V0m = model->V0 - b->eps5[4];
+  v_grid(ctx, m2, V0p, v_pool.data() + (m2 + 1));
+  v_grid(ctx, m2, b->mode == HADI_MODE_JACOBIAN_CENTRAL ? V0m : model->V0, v_pool.data() + 2 * (m2 + 1));
+  int idx_v0 = find_node(v_pool.data(), m2 + 1, model->V0);
+  if (idx_v0 < 0) idx_v0 = 0;
+  int idx_v1 = find_node(v_pool.data() + (m2 + 1), m2 + 1, V0p);
+  if (idx_v1 < 0) idx_v1 = 0;
+  int idx_v2 = find_node(v_pool.data() + 2 * (m2 + 1), m2 + 1, V0m);
+  if (idx_v2 < 0) idx_v2 = 0;
+  int br_lo = 0, br_hi = 0;
+  double br_w = 0.0;
+  v0_bracket(v_pool.data(), m2, V0p, &br_lo, &br_hi, &br_w);
+  for (HadiItem& it : b->h_items) {
+    const int col = (b->item_begin + it.out) % nc;
+    it.kappa = model->kappa;
+    it.eta = model->eta;
+    it.sigma = model->sigma;
+    it.rho = model->rho;
+    if (col == 1) it.kappa += b->eps5[0];
+    if (col == 2) it.eta += b->eps5[1];
+    if (col == 3) it.sigma += b->eps5[2];
+    if (col == 4) it.rho += b->eps5[3];
+    if (col == 6) it.kappa -= b->eps5[0];
+    if (col == 7) it.eta -= b->eps5[1];
+    if (col == 8) it.sigma -= b->eps5[2];
+    if (col == 9) it.rho -= b->eps5[3];
+    it.idx_v = (col == 5) ? idx_v1 : (col == 10) ? idx_v2 : idx_v0;
+    it.aux = br_lo | (br_hi << 16);
+  }
+  const size_t bytes_items = sizeof(HadiItem) * b->h_items.size(), bytes_v = sizeof(double) * v_pool.size();
+  if (bytes_items) std::memcpy(b->h_stage + b->o_items, b->h_items.data(), bytes_items);
+  std::memcpy(b->h_stage + b->o_v, v_pool.data(), bytes_v);
+  cudaError_t e = cudaSuccess;
+  if (bytes_items) e = cudaMemcpyAsync(b->d_stage + b->o_items, b->h_stage + b->o_items, bytes_items, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(b->d_stage + b->o_v, b->h_stage + b->o_v, bytes_v, cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "H2D (model update)");
+  ctx->h2d_bytes += (long long)(bytes_items + bytes_v);
+  return HADI_OK;
+}
 
 int hadi_batch_launch(hadi_batch* b) {
   if (!b) return HADI_ERR_ARG;
@@ -1221,94 +1291,130 @@ int hadi_lm_update(int n, const double* J, const double* r, double lambda, doubl
   return hadi_solve5(A, g, delta);
 }
 
-// The same over the context's NCCL communicator, with no host hop in the exchange: this rank's kernel writes its
-// item values straight into its slot of the gather buffer (hadi_publish stores through L.out_values), one in-place
-// ncclAllGather runs behind the kernel on the same stream, one device-to-host copy brings every rank's values back.
-static int solve_all_nccl(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
-                          const hadi_point* points, int mode, const double* eps5, double* all, float* ms) {
-  const int nc = n_columns(mode), vpi = values_per_item(mode);
-  const int total = n * nc, W = ctx->nccl_world, R = ctx->nccl_rank;
-  std::vector<int> costs((size_t)std::max(total, 1)), counts(W), displs(W);
-  hadi_item_costs(num, n, points, mode, costs.data());
-  int my_begin = 0, my_end = 0;
-  size_t mx = 1;
-  for (int r = 0; r < W; ++r) {
-    int b, e;
-    hadi_partition(total, costs.data(), W, r, &b, &e);
-    displs[r] = b * vpi;
-    counts[r] = (e - b) * vpi;
-    mx = std::max(mx, (size_t)counts[r]);
-    if (r == R) { my_begin = b; my_end = e; }
-  }
-  cudaSetDevice(ctx->device);
-  if (ctx->gather_cap < mx) {
-    cudaStreamSynchronize(ctx->stream);
-    if (ctx->d_gather) cudaFree(ctx->d_gather);
-    if (ctx->h_gather) cudaFreeHost(ctx->h_gather);
-    ctx->d_gather = nullptr; ctx->h_gather = nullptr; ctx->gather_cap = 0;
-    const size_t cap = std::max<size_t>(mx + mx / 4, 1024);
-    if (cudaMalloc(&ctx->d_gather, sizeof(double) * cap * W) != cudaSuccess ||
-        cudaMallocHost(&ctx->h_gather, sizeof(double) * cap * W) != cudaSuccess)
-      return cuda_fail(ctx, cudaGetLastError(), "gather buffers");
-    ctx->gather_cap = cap;
-  }
+// A prepared batch plus what the exchange step needs: this rank's slice of the work items, the per-rank counts, and
+// how the values come back — directly (one GPU), through the context's NCCL communicator (the kernel epilogue
+// publishes into this rank's slot of the device gather buffer, one in-place ncclAllGather behind the kernel on the same
+// stream, one device-to-host copy: no host hop in the exchange), or through the caller's hadi_comm hook.
+struct ShardedBatch {
   hadi_batch* b = nullptr;
-  int rc = hadi_batch_create_ex(ctx, model, num, n, points, mode, eps5, my_begin, my_end, &b);
+  int vpi = 1, world = 1, rank = 0;
+  bool nccl = false;
+  const hadi_comm* hook = nullptr;
+  std::vector<int> counts, displs;
+  size_t mx = 1;                 // longest slice in doubles (the all-gather's element count)
+  std::vector<double> mine;      // hook path only
+};
+
+static void sharded_destroy(ShardedBatch* sb) {
+  if (sb->b) hadi_batch_destroy(sb->b);
+  sb->b = nullptr;
+}
+
+static int sharded_create(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
+                          const hadi_point* points, int mode, const double* eps5, const hadi_comm* comm,
+                          ShardedBatch* sb) {
+  const int nc = n_columns(mode);
+  const int total = n * nc;
+  sb->vpi = values_per_item(mode);
+  sb->hook = (comm && comm->world > 1) ? comm : nullptr;
+  sb->nccl = !sb->hook && ctx->nccl && ctx->nccl_world > 1;
+  sb->world = sb->hook ? comm->world : sb->nccl ? ctx->nccl_world : 1;
+  sb->rank = sb->hook ? comm->rank : sb->nccl ? ctx->nccl_rank : 0;
+  int my_begin = 0, my_end = total;
+  sb->counts.assign(sb->world, total * sb->vpi);
+  sb->displs.assign(sb->world, 0);
+  sb->mx = std::max<size_t>((size_t)total * sb->vpi, 1);
+  if (sb->world > 1) {
+    std::vector<int> costs((size_t)std::max(total, 1));
+    hadi_item_costs(num, n, points, mode, costs.data());
+    sb->mx = 1;
+    for (int r = 0; r < sb->world; ++r) {
+      int b, e;
+      hadi_partition(total, costs.data(), sb->world, r, &b, &e);
+      sb->displs[r] = b * sb->vpi;
+      sb->counts[r] = (e - b) * sb->vpi;
+      sb->mx = std::max(sb->mx, (size_t)sb->counts[r]);
+      if (r == sb->rank) { my_begin = b; my_end = e; }
+    }
+  }
+  if (sb->hook) sb->mine.resize((size_t)std::max(sb->counts[sb->rank], 1));
+  if (sb->nccl) {
+    cudaSetDevice(ctx->device);
+    if (ctx->gather_cap < sb->mx) {
+      cudaStreamSynchronize(ctx->stream);
+      if (ctx->d_gather) cudaFree(ctx->d_gather);
+      if (ctx->h_gather) cudaFreeHost(ctx->h_gather);
+      ctx->d_gather = nullptr; ctx->h_gather = nullptr; ctx->gather_cap = 0;
+      const size_t cap = std::max<size_t>(sb->mx + sb->mx / 4, 4096);
+      if (cudaMalloc(&ctx->d_gather, sizeof(double) * cap * sb->world) != cudaSuccess ||
+          cudaMallocHost(&ctx->h_gather, sizeof(double) * cap * sb->world) != cudaSuccess)
+        return cuda_fail(ctx, cudaGetLastError(), "gather buffers");
+      ctx->gather_cap = cap;
+    }
+  }
+  return hadi_batch_create_ex(ctx, model, num, n, points, mode, eps5, my_begin, my_end, &sb->b);
+}
+
+// One solver call on a prepared sharded batch: `model` != nullptr re-aims it first (hadi_batch_update_model).
+// all[total items * values per item] on every rank.
+static int sharded_solve(hadi_ctx* ctx, ShardedBatch* sb, const hadi_model* model, double* all, float* ms) {
+  hadi_batch* b = sb->b;
+  int rc = model ? hadi_batch_update_model(b, model) : HADI_OK;
   if (rc != HADI_OK) return rc;
-  b->L.out_values = ctx->d_gather + (size_t)R * mx;   // the kernel epilogue publishes into the gather buffer
-  rc = hadi_batch_launch(b);
-  if (rc == HADI_OK) {
-    const ncclResult_t nr = nccl_api().AllGather(ctx->d_gather + (size_t)R * mx, ctx->d_gather, mx, ncclDouble,
-                                                 ctx->nccl, ctx->stream);
-    if (nr != ncclSuccess) rc = nccl_fail(ctx, nr, "ncclAllGather");
+  if (sb->world <= 1) {
+    rc = hadi_batch_launch(b);
+    if (rc == HADI_OK) rc = hadi_batch_fetch(b, all);
+  } else if (sb->hook) {
+    rc = hadi_batch_launch(b);
+    if (rc == HADI_OK) rc = hadi_batch_fetch(b, sb->mine.data());
+    if (rc == HADI_OK) {
+      if (!sb->hook->allgather) return fail(ctx, HADI_ERR_COMM, "no allgather hook");
+      if (sb->hook->allgather(sb->hook->user, sb->mine.data(), sb->counts[sb->rank], all, sb->counts.data(),
+                              sb->displs.data(), sb->world) != 0)
+        return fail(ctx, HADI_ERR_COMM, "allgather failed");
+    }
+  } else {
+    const size_t mx = sb->mx;
+    const int W = sb->world, R = sb->rank;
+    if (ctx->gather_cap < mx) return fail(ctx, HADI_ERR_COMM, "gather buffer smaller than the batch (context shared between calibrations?)");
+    b->L.out_values = ctx->d_gather + (size_t)R * mx;   // the kernel epilogue publishes into the gather buffer
+    rc = hadi_batch_launch(b);
+    if (rc == HADI_OK) {
+      const ncclResult_t nr = nccl_api().AllGather(ctx->d_gather + (size_t)R * mx, ctx->d_gather, mx, ncclDouble,
+                                                   ctx->nccl, ctx->stream);
+      if (nr != ncclSuccess) rc = nccl_fail(ctx, nr, "ncclAllGather");
+    }
+    if (rc == HADI_OK) {
+      cudaError_t e = cudaMemcpyAsync(ctx->h_gather, ctx->d_gather, sizeof(double) * mx * W, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(b->h_values, b->L.reruns, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+      if (e != cudaSuccess) rc = cuda_fail(ctx, e, "gather D2H");
+      ctx->d2h_bytes += (long long)(sizeof(double) * mx * W);
+    }
+    if (rc == HADI_OK) {
+      for (int r = 0; r < W; ++r)
+        if (sb->counts[r] > 0)
+          std::memcpy(all + sb->displs[r], ctx->h_gather + (size_t)r * mx, sizeof(double) * (size_t)sb->counts[r]);
+      unsigned long long rr = 0;
+      std::memcpy(&rr, b->h_values, sizeof rr);
+      b->reruns = (long long)rr;
+      ctx->exact_reruns += (long long)rr;
+    }
   }
-  if (rc == HADI_OK) {
-    cudaError_t e = cudaMemcpyAsync(ctx->h_gather, ctx->d_gather, sizeof(double) * mx * W, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(b->h_values, b->L.reruns, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) rc = cuda_fail(ctx, e, "gather D2H");
-    ctx->d2h_bytes += (long long)(sizeof(double) * mx * W);
-  }
-  if (rc == HADI_OK) {
-    for (int r = 0; r < W; ++r)
-      if (counts[r] > 0) std::memcpy(all + displs[r], ctx->h_gather + (size_t)r * mx, sizeof(double) * (size_t)counts[r]);
-    unsigned long long rr = 0;
-    std::memcpy(&rr, b->h_values, sizeof rr);
-    ctx->exact_reruns += (long long)rr;
-    if (ms) hadi_batch_elapsed_ms(b, ms);
-  }
-  hadi_batch_destroy(b);
+  if (rc == HADI_OK && ms) hadi_batch_elapsed_ms(b, ms);
   return rc;
 }
 
-// Solve the items of [0, n*nc) across the ranks of `comm` and return every item value on every rank
-// (all[n * nc * values_per_item(mode)]).
+// Solve the items of [0, n*nc) across the ranks (the context's communicator, or `comm`) and return every item value
+// on every rank (all[n * nc * values_per_item(mode)]).
 static int solve_all(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
                      const hadi_point* points, int mode, const double* eps5, const hadi_comm* comm, double* all,
                      float* ms) {
-  const int nc = n_columns(mode), vpi = values_per_item(mode);
-  const int total = n * nc;
-  if ((!comm || comm->world <= 1) && ctx->nccl && ctx->nccl_world > 1)
-    return solve_all_nccl(ctx, model, num, n, points, mode, eps5, all, ms);
-  if (!comm || comm->world <= 1)
-    return run_items(ctx, model, num, n, points, mode, eps5, 0, total, all, nullptr, nullptr, ms);
-  std::vector<int> costs((size_t)std::max(total, 1)), counts(comm->world), displs(comm->world);
-  hadi_item_costs(num, n, points, mode, costs.data());
-  int my_begin = 0, my_end = 0;
-  for (int r = 0; r < comm->world; ++r) {
-    int b, e;
-    hadi_partition(total, costs.data(), comm->world, r, &b, &e);
-    displs[r] = b * vpi;
-    counts[r] = (e - b) * vpi;
-    if (r == comm->rank) { my_begin = b; my_end = e; }
-  }
-  std::vector<double> mine((size_t)std::max(counts[comm->rank], 1));
-  int rc = run_items(ctx, model, num, n, points, mode, eps5, my_begin, my_end, mine.data(), nullptr, nullptr, ms);
-  if (rc != HADI_OK) return rc;
-  if (!comm->allgather) return fail(ctx, HADI_ERR_COMM, "no allgather hook");
-  if (comm->allgather(comm->user, mine.data(), counts[comm->rank], all, counts.data(), displs.data(), comm->world) != 0)
-    return fail(ctx, HADI_ERR_COMM, "allgather failed");
-  return HADI_OK;
+  ShardedBatch sb;
+  int rc = sharded_create(ctx, model, num, n, points, mode, eps5, comm, &sb);
+  if (rc == HADI_OK) rc = sharded_solve(ctx, &sb, nullptr, all, ms);
+  sharded_destroy(&sb);
+  return rc;
 }
 
 // src/heston_calibration.cpp:2692-2831 (multi-maturity; the single-maturity twin at :204-417 is the
@@ -1340,9 +1446,19 @@ int hadi_calibrate_ex(hadi_ctx* ctx, const hadi_model* initial, const hadi_numer
   bool converged = false;
   int iters = 0, solves = 0;
   double final_error = 100.0, delta_norm = 0.0, gpu_ms = 0.0;
+  // the two batches of the loop (Jacobian, candidate prices) are built once; every iteration only re-aims them at
+  // the current parameters (hadi_batch_update_model)
+  ShardedBatch sb_jac, sb_price;
+  struct Guard {
+    ShardedBatch *a, *b;
+    ~Guard() { sharded_destroy(a); sharded_destroy(b); }
+  } guard{&sb_jac, &sb_price};
+  int rc = sharded_create(ctx, &cur, num, n, points, jo->mode, jo->eps, comm, &sb_jac);
+  if (rc == HADI_OK) rc = sharded_create(ctx, &cur, num, n, points, HADI_MODE_PRICE, kNoEps, comm, &sb_price);
+  if (rc != HADI_OK) return rc;
   for (int iter = 0; iter < opt->max_iter && !converged; ++iter) {
     float ms = 0.f;
-    int rc = solve_all(ctx, &cur, num, n, points, jo->mode, jo->eps, comm, vals.data(), &ms);
+    rc = sharded_solve(ctx, &sb_jac, iter == 0 ? nullptr : &cur, vals.data(), &ms);
     if (rc != HADI_OK) return rc;
     gpu_ms += ms;
     solves += jcols * n;
@@ -1376,7 +1492,7 @@ int hadi_calibrate_ex(hadi_ctx* ctx, const hadi_model* initial, const hadi_numer
       iters = iter + 1;
       break;
     }
-    rc = solve_all(ctx, &nw, num, n, points, HADI_MODE_PRICE, kNoEps, comm, nv.data(), &ms);
+    rc = sharded_solve(ctx, &sb_price, &nw, nv.data(), &ms);
     if (rc != HADI_OK) return rc;
     gpu_ms += ms;
     solves += n;

@@ -37,7 +37,7 @@ EXPORTS = [
     "hadi_batch_create_ex", "hadi_batch_values_per_item", "hadi_jacobian_assemble_ex", "hadi_jacobian_v0_weight",
     "hadi_jacobian_batch_ex", "hadi_calibrate_ex", "hadi_plan_schedule", "hadi_exact_reruns",
     "hadi_batch_exact_reruns", "hadi_nccl_unique_id", "hadi_comm_init", "hadi_comm_finalize", "hadi_comm_world",
-    "hadi_comm_rank", "hadi_price_batch_sharded", "hadi_jacobian_batch_sharded",
+    "hadi_comm_rank", "hadi_price_batch_sharded", "hadi_jacobian_batch_sharded", "hadi_batch_update_model",
 ]
 
 
@@ -121,6 +121,7 @@ def lib():
                                                C.POINTER(Point), _dp]
         L.hadi_jacobian_batch_sharded.argtypes = [C.c_void_p, C.POINTER(Model), C.POINTER(Numerics), C.c_int,
                                                   C.POINTER(Point), C.POINTER(JacobianOptions), _dp, _dp]
+        L.hadi_batch_update_model.argtypes = [C.c_void_p, C.POINTER(Model)]
         L.hadi_exact_reruns.argtypes = [C.c_void_p]
         L.hadi_exact_reruns.restype = C.c_longlong
         L.hadi_batch_exact_reruns.argtypes = [C.c_void_p]
@@ -525,6 +526,10 @@ class Batch:
                                               begin, end, C.byref(self._h)))
         self.n_items = lib().hadi_batch_num_items(self._h)
         self.values_per_item = lib().hadi_batch_values_per_item(self._h)
+
+    def update_model(self, model):
+        """Re-aim the prepared batch at new (kappa, eta, sigma, rho, V0); S0, r_d, r_f as at creation."""
+        self.ctx._check(lib().hadi_batch_update_model(self._h, C.byref(model)))
 
     def launch(self):
         self.ctx._check(lib().hadi_batch_launch(self._h))

@@ -662,3 +662,38 @@ def test_tensor_memory_relay_kernel_equals_plain_load_kernel(hadi, ctx, oracle, 
             o = oracle.solve(strikes[n // 2], Ns[n // 2], 1.0 / Ns[n // 2], m1=100, m2=50, theta=0.8, style=style,
                              divs=dv, payoff_put=0, want_U=False, want_lambda=False, **BASE)
             assert tm["prices"][n // 2] == o["price"]
+
+
+def test_batch_update_model_equals_fresh_batch(hadi, ctx):
+    """hadi_batch_update_model: a prepared batch re-aimed at new (kappa, eta, sigma, rho, V0) — the V0 change moves the
+    v-grids and the price-pick row — publishes the values of a batch built for those parameters, in every mode;
+    changing S0 / r_d / r_f is refused."""
+    K = [90.0 + 2.0 * k for k in range(12)]
+    T = [1.0 + 0.25 * (k % 3) for k in range(12)]
+    N = [20 + 5 * (k % 3) for k in range(12)]
+    pts, n = hadi.make_points(K, T, N)
+    a = hadi.make_model(**BASE)
+    bpar = dict(BASE, kappa=2.25, eta=0.055, sigma=0.41, rho=-0.35, V0=0.0625)
+    bmdl = hadi.make_model(**bpar)
+    for num in (hadi.make_numerics(50, 25, 0.8), hadi.make_numerics(100, 50, 0.8, hadi.AMERICAN, hadi.CALL, hadi.DOUGLAS, DIVS)):
+        for mode in (hadi.MODE_PRICE, hadi.MODE_JACOBIAN, hadi.MODE_JACOBIAN_INTERP, hadi.MODE_JACOBIAN_CENTRAL):
+            bt = ctx.batch(a, num, pts, n, mode=mode)
+            bt.launch()
+            bt.fetch()
+            bt.update_model(bmdl)
+            bt.launch()
+            got = bt.fetch().copy()
+            fresh = ctx.batch(bmdl, num, pts, n, mode=mode)
+            fresh.launch()
+            want = fresh.fetch().copy()
+            assert np.array_equal(got, want), mode
+            bt.update_model(a)          # and back
+            bt.launch()
+            back = bt.fetch().copy()
+            first = ctx.batch(a, num, pts, n, mode=mode)
+            first.launch()
+            assert np.array_equal(back, first.fetch())
+            with pytest.raises(hadi.HadiError):
+                bt.update_model(hadi.make_model(**dict(BASE, r_d=0.03)))
+            for x in (bt, fresh, first):
+                x.destroy()
