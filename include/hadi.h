@@ -61,6 +61,12 @@ extern "C" {
 #define HADI_PUT 1               /* put PAYOFF under the reference's call boundary vectors */
 #define HADI_DOUGLAS 0
 #define HADI_CRAIG_SNEYD 1
+/* opt-in extensions beyond the reference's device path.  PARITY UNPINNED: the reference
+ * has no such code path; the CPU restatement in oracle/hadi_oracle.c is the definition the GPU path is tested against. */
+#define HADI_BC_REFERENCE_CALL 0   /* the reference's boundary vectors b1, b2 (call asymptotics; src/BoundaryConditions.hpp:7-12) */
+#define HADI_BC_PUT 1              /* put-correct set: b1 = b2 = 0 and Dirichlet U(s_0, v, tau) = K exp(-r_d tau) after every step */
+#define HADI_DIVIDENDS_DEVICE 0    /* the device path's schedule: one dividend per step at most (quirk Q7, src/device_solver.hpp:432-516) */
+#define HADI_DIVIDENDS_ALL 1       /* the host solver's schedule: every dividend dated inside the step, in order (src/solver.hpp:363) */
 
 typedef struct hadi_ctx hadi_ctx;
 typedef struct hadi_batch hadi_batch;
@@ -95,6 +101,8 @@ typedef struct {
   const double* dividend_dates;
   const double* dividend_amounts;
   const double* dividend_percentages;
+  int boundary;            /* HADI_BC_REFERENCE_CALL (0, the parity path) | HADI_BC_PUT (Douglas only) */
+  int dividend_schedule;   /* HADI_DIVIDENDS_DEVICE (0, the parity path) | HADI_DIVIDENDS_ALL */
 } hadi_numerics;
 
 typedef struct {

@@ -350,9 +350,10 @@ static void solve_a2(ho_ws *w, double *x, const double *b) {
 
 /* device path: src/hes_boundary_kernels.hpp:41-75 (b1 at index m1*(j+1): quirk Q3; b2 from i=0).
  * host path (Craig-Sneyd): src/BoundaryConditions.hpp:52-92 (b2 from i=1: quirk Q4). */
-static void build_bounds(ho_ws *w, double r_d, double r_f, int N, double dt, int host_variant) {
+static void build_bounds(ho_ws *w, double r_d, double r_f, int N, double dt, int host_variant, int bc) {
   const int m1 = w->m1, m2 = w->m2, P = w->P;
   for (int p = 0; p < P; ++p) w->b[p] = w->b1[p] = w->b2[p] = 0.0;
+  if (bc == 1) return;   /* put-correct set (extension): no inflow terms at s_max and v_max */
   const double ef = exp(-r_f * dt * (N - 1));
   for (int j = 0; j <= m2; ++j) w->b1[m1 * (j + 1)] = (r_d - r_f) * w->s[m1] * ef;
   for (int i = host_variant ? 1 : 0; i <= m1; ++i) w->b2[P - m1 - 1 + i] = -0.5 * r_d * w->s[i] * ef;
@@ -395,7 +396,7 @@ static void dividend_jump(ho_ws *w, double *U, double amount, double pct) {
 
 /* src/device_solver.hpp:194-266 (European), :276-374 (American), :384-641 (dividends), :652-942 (both).
  * U holds the payoff on entry and the solution on exit. */
-static void douglas(ho_ws *w, const ho_numerics *num, int N, double dt, double r_f, double *U) {
+static void douglas(ho_ws *w, const ho_numerics *num, int N, double dt, double r_f, double r_d, double K, double *U) {
   const int P = w->P, m1 = w->m1;
   const double theta = num->theta;
   const int am = num->style == 1;
@@ -403,7 +404,14 @@ static void douglas(ho_ws *w, const ho_numerics *num, int N, double dt, double r
   if (am)
     for (int p = 0; p < P; ++p) w->lam[p] = 0;
   for (int n = 1; n <= N; ++n) {
-    if (num->nd > 0) {
+    if (num->nd > 0 && num->div_all) {
+      /* extension: the host solver's schedule (src/solver.hpp:363), every dividend dated inside the step */
+      const double t = n * dt;
+      while (div_idx < num->nd && t <= num->div_dates[div_idx] && num->div_dates[div_idx] < (n + 1) * dt) {
+        dividend_jump(w, U, num->div_amounts[div_idx], num->div_pcts[div_idx]);
+        div_idx++;
+      }
+    } else if (num->nd > 0) {
       /* one dividend per step at most, rank-0 index logic: src/device_solver.hpp:432-516 (quirk Q7) */
       const double t = n * dt;
       const int hit = (div_idx < num->nd && t <= num->div_dates[div_idx] && num->div_dates[div_idx] < (n + 1) * dt);
@@ -427,6 +435,11 @@ static void douglas(ho_ws *w, const ho_numerics *num, int N, double dt, double r
       solve_a1(w, w->Y1, w->Y0);
       for (int p = 0; p < P; ++p) w->Y1[p] = w->Y1[p] + theta * dt * (w->b2[p] * e1 - (w->R2[p] + w->b2[p] * e0));
       solve_a2(w, U, w->Y1);
+    }
+    if (num->bc == 1) {
+      /* extension: Dirichlet value of a put at s_0 (row i = 0 of A1 is the identity row, so nothing else moves it) */
+      const double g = K * exp(-r_d * dt * n);
+      for (int j = 0; j <= w->m2; ++j) U[j * (m1 + 1)] = g;
     }
     if (am) {
       /* Ikonen-Toivanen projection: src/device_solver.hpp:358-372 */
@@ -487,12 +500,12 @@ static void build_all(ho_ws *w, const ho_model *mdl, const ho_numerics *num, dou
   build_a2(w, mdl->r_d, mdl->kappa, mdl->eta, mdl->sigma, num->theta, dt);
 }
 
-static int solve_ws(ho_ws *w, const ho_model *mdl, const ho_numerics *num, int N, double dt, double *U) {
+static int solve_ws(ho_ws *w, const ho_model *mdl, const ho_numerics *num, int N, double dt, double K, double *U) {
   memcpy(U, w->U0, sizeof(double) * (size_t)w->P);
   if (num->scheme == 1)
     craig_sneyd(w, num, N, dt, mdl->r_f, U);
   else
-    douglas(w, num, N, dt, mdl->r_f, U);
+    douglas(w, num, N, dt, mdl->r_f, mdl->r_d, K, U);
   return 0;
 }
 
@@ -512,9 +525,9 @@ int ho_solve(const ho_model *mdl, const ho_numerics *num, double K, int N, doubl
   ho_ws *w = ws_new(num->m1, num->m2);
   double *U = dalloc(w->P);
   setup_option(w, mdl, num, K, V0_for_grid);
-  build_bounds(w, mdl->r_d, mdl->r_f, N, dt, num->scheme == 1);
+  build_bounds(w, mdl->r_d, mdl->r_f, N, dt, num->scheme == 1, num->bc);
   build_all(w, mdl, num, dt);
-  solve_ws(w, mdl, num, N, dt, U);
+  solve_ws(w, mdl, num, N, dt, K, U);
   const int rc = pick(w, mdl->S0, V0_for_grid, U, price);
   if (U_out) memcpy(U_out, U, sizeof(double) * (size_t)w->P);
   if (lambda_out) memcpy(lambda_out, w->lam, sizeof(double) * (size_t)w->P);
@@ -544,9 +557,9 @@ int ho_jacobian_batch(const ho_model *mdl, const ho_numerics *num, int n, const 
     const int N = Ns[k];
     const double dt = dts[k];
     setup_option(w, mdl, num, strikes[k], mdl->V0);
-    build_bounds(w, mdl->r_d, mdl->r_f, N, dt, num->scheme == 1);
+    build_bounds(w, mdl->r_d, mdl->r_f, N, dt, num->scheme == 1, num->bc);
     build_all(w, mdl, num, dt);
-    solve_ws(w, mdl, num, N, dt, U);
+    solve_ws(w, mdl, num, N, dt, strikes[k], U);
     double base_price = 0.0;
     if (pick(w, mdl->S0, mdl->V0, U, &base_price) != 0) rc = -1;
     base[k] = base_price;
@@ -559,7 +572,7 @@ int ho_jacobian_batch(const ho_model *mdl, const ho_numerics *num, int n, const 
         case 3: m.rho += eps; break;
       }
       build_all(w, &m, num, dt);
-      solve_ws(w, &m, num, N, dt, U);
+      solve_ws(w, &m, num, N, dt, strikes[k], U);
       double pert = 0.0;
       pick(w, mdl->S0, mdl->V0, U, &pert);
       J[k * 5 + param] = (pert - base_price) / eps;
@@ -568,7 +581,7 @@ int ho_jacobian_batch(const ho_model *mdl, const ho_numerics *num, int n, const 
       const double V0p = mdl->V0 + eps;
       ho_grid_v(w->m2, 5.0, V0p, 5.0 / 500, w->v, w->dv);
       build_all(w, mdl, num, dt);
-      solve_ws(w, mdl, num, N, dt, U);
+      solve_ws(w, mdl, num, N, dt, strikes[k], U);
       double pert = 0.0;
       pick(w, mdl->S0, V0p, U, &pert);
       J[k * 5 + 4] = (pert - base_price) / eps;

@@ -29,6 +29,12 @@ typedef struct {
   int scheme;                           /* 0 Douglas (device path), 1 Craig-Sneyd (host path) */
   int nd;                               /* number of dividends */
   const double *div_dates, *div_amounts, *div_pcts;
+  /* opt-in extensions beyond the reference's device path (PARITY UNPINNED: the
+   * reference has no such code path, the restatement below is the definition both sides are tested against) */
+  int bc;                               /* 0 reference call boundary vectors; 1 put-correct set: b1 = b2 = 0 and
+                                           Dirichlet U(s_0, v, tau) = K exp(-r_d tau) after every step */
+  int div_all;                          /* 0 device schedule (one dividend per step at most, quirk Q7); 1 every
+                                           dividend whose date falls in the step, in order (src/solver.hpp:363) */
 } ho_numerics;
 
 /* grids: src/grid.cpp:16-96, src/grid_pod.hpp:25-87 */

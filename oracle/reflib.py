@@ -191,7 +191,7 @@ class _Model(C.Structure):
 class _Numerics(C.Structure):
     _fields_ = [("m1", C.c_int), ("m2", C.c_int), ("theta", C.c_double), ("style", C.c_int),
                 ("payoff_put", C.c_int), ("scheme", C.c_int), ("nd", C.c_int), ("div_dates", _dp),
-                ("div_amounts", _dp), ("div_pcts", _dp)]
+                ("div_amounts", _dp), ("div_pcts", _dp), ("bc", C.c_int), ("div_all", C.c_int)]
 
 
 class _LmOpts(C.Structure):
@@ -231,16 +231,16 @@ class OracleLib:
 
     @staticmethod
     def _mk(S0, V0, r_d, r_f, rho, sigma, kappa, eta, m1, m2, theta, style=0, payoff_put=0, scheme=0,
-            divs=None):
+            divs=None, bc=0, div_all=0):
         mdl = _Model(S0, V0, r_d, r_f, kappa, eta, sigma, rho)
         keep = []
         if divs is not None and len(divs[0]) > 0:
             arrs = [np.ascontiguousarray(x, dtype=np.float64) for x in divs]
             keep = arrs
             num = _Numerics(m1, m2, theta, style, payoff_put, scheme, arrs[0].size, _d(arrs[0]),
-                            _d(arrs[1]), _d(arrs[2]))
+                            _d(arrs[1]), _d(arrs[2]), bc, div_all)
         else:
-            num = _Numerics(m1, m2, theta, style, payoff_put, scheme, 0, None, None, None)
+            num = _Numerics(m1, m2, theta, style, payoff_put, scheme, 0, None, None, None, bc, div_all)
         return mdl, num, keep
 
     def grid(self, m1, m2, K, S0, V0):

@@ -253,6 +253,10 @@ bool valid_numerics(const hadi_numerics* num) {
   if (num->num_dividends > 0 &&
       (!num->dividend_dates || !num->dividend_amounts || !num->dividend_percentages))
     return false;
+  // opt-in extensions (parity unpinned): the reference defines Craig-Sneyd with its call boundary vectors only
+  if (num->boundary != HADI_BC_REFERENCE_CALL && num->boundary != HADI_BC_PUT) return false;
+  if (num->boundary == HADI_BC_PUT && num->scheme == HADI_CRAIG_SNEYD) return false;
+  if (num->dividend_schedule != HADI_DIVIDENDS_DEVICE && num->dividend_schedule != HADI_DIVIDENDS_ALL) return false;
   return true;
 }
 
@@ -730,6 +734,8 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
     it.style = num->style;
     it.payoff = num->payoff;
     it.nd = num->num_dividends;
+    it.bc = num->boundary;
+    it.div_all = num->dividend_schedule;
     if (use_dev_pool) {
       const auto dkey = std::make_tuple(m1, bits(pt.strike), bits(model->S0));
       auto dit = ctx->s_dev.find(dkey);
@@ -770,6 +776,9 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
     if (eit == e_index.end()) {
       const int off = (int)e_pool.size();
       for (int nn = 0; nn <= pt.time_steps; ++nn) e_pool.push_back(std::exp(model->r_f * pt.delta_t * nn));
+      // discount table of the put-correct boundary set (HADI_BC_PUT): exp(-r_d*dt*n) behind the r_f table
+      if (num->boundary == HADI_BC_PUT)
+        for (int nn = 0; nn <= pt.time_steps; ++nn) e_pool.push_back(std::exp(-model->r_d * pt.delta_t * nn));
       e_index.emplace(ekey, off);
       it.e_off = off;
     } else {

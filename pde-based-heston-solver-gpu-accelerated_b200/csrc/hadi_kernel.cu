@@ -250,11 +250,17 @@ __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiI
   int div_cur = 0;
   bool stopped = false;
   if (it.nd > 0)   // dividend queue position after the steps another CTA ran
-    for (int n = 1; n < n0; ++n) hadi_dividend_at(n, it.dt, it.nd, L.div_dates, div_cur);
+    for (int n = 1; n < n0; ++n) {
+      if (it.div_all) { while (hadi_dividend_next(n, it.dt, it.nd, L.div_dates, div_cur) >= 0) {} }
+      else hadi_dividend_at(n, it.dt, it.nd, L.div_dates, div_cur);
+    }
   for (int n = n0; n <= n1; ++n) {
     if (it.nd > 0) {
-      const int hit = hadi_dividend_at(n, it.dt, it.nd, L.div_dates, div_cur);
-      if (hit >= 0) {  // uniform across the CTA
+      // device schedule: one dividend per step at most; extension: every dividend dated inside the step, in order
+      for (;;) {
+        const int hit = it.div_all ? hadi_dividend_next(n, it.dt, it.nd, L.div_dates, div_cur)
+                                   : hadi_dividend_at(n, it.dt, it.nd, L.div_dates, div_cur);
+        if (hit < 0) break;  // uniform across the CTA
         hadi_phase_div1(w, L.div_amounts[hit], L.div_pcts[hit], tid, NT);
         HADI_SYNC();
         HADI_STOP(1)
@@ -266,7 +272,11 @@ __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiI
           HADI_SYNC();
         }
         HADI_STOP(3)
+        if (!it.div_all) break;
       }
+#ifdef HADI_DEBUG_STOP
+      if (stopped) break;
+#endif
     }
     HADI_TICK(0)
 #ifdef HADI_DEBUG_LAM
@@ -313,6 +323,7 @@ __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiI
     } else {
       hadi_phase_solve_a2<M1, M2, EXACT>(it, w, tid, NT, bad);
     }
+    if (it.bc && tid * w.line_mul + w.line_off == 0) hadi_dirichlet_col0(w, it.K * eg[it.N + 1 + n]);
     HADI_SYNC();
     HADI_TICK(4)
     HADI_STOP(7)
@@ -730,6 +741,7 @@ __device__ __forceinline__ bool hadi_cluster_solve(const HadiLaunch& L, const Ha
       hadi_phase_rhs2<0, 0>(it, w, e0, e1, gtid, gnt);
       hadi_csync();
       hadi_phase_solve_a2<0, 0, EXACT>(it, w, tid, NT, bad);
+      if (it.bc && tid * w.line_mul + w.line_off == 0) hadi_dirichlet_col0(w, it.K * eg[it.N + 1 + n]);
       hadi_csync();
       if (it.style == 1) {
         hadi_phase_project<0, 0, EXACT, HADI_CHP>(it, w, rdt, gtid, gnt, bad);

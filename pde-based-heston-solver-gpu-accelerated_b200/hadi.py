@@ -21,6 +21,8 @@ OK, ERR_ARG, ERR_GRID, ERR_CUDA, ERR_SMEM, ERR_COMM, ERR_NOMEM = 0, -1, -2, -3, 
 EUROPEAN, AMERICAN = 0, 1
 CALL, PUT = 0, 1
 DOUGLAS, CRAIG_SNEYD = 0, 1
+BC_REFERENCE_CALL, BC_PUT = 0, 1
+DIVIDENDS_DEVICE, DIVIDENDS_ALL = 0, 1
 MODE_PRICE, MODE_JACOBIAN, MODE_JACOBIAN_INTERP, MODE_JACOBIAN_CENTRAL = 0, 1, 2, 3
 ITEMS_PER_OPTION = {0: 1, 1: 6, 2: 5, 3: 11}
 VALUES_PER_ITEM = {0: 1, 1: 1, 2: 3, 3: 1}
@@ -53,7 +55,8 @@ class Point(C.Structure):
 class Numerics(C.Structure):
     _fields_ = [("m1", C.c_int), ("m2", C.c_int), ("theta", C.c_double), ("style", C.c_int),
                 ("payoff", C.c_int), ("scheme", C.c_int), ("num_dividends", C.c_int),
-                ("dividend_dates", _dp), ("dividend_amounts", _dp), ("dividend_percentages", _dp)]
+                ("dividend_dates", _dp), ("dividend_amounts", _dp), ("dividend_percentages", _dp),
+                ("boundary", C.c_int), ("dividend_schedule", C.c_int)]
 
 
 class LmOptions(C.Structure):
@@ -221,19 +224,23 @@ def make_points(strikes, maturities, time_steps, delta_t=None):
 class _NumKeep:
     """Numerics struct plus the numpy arrays its pointers refer to."""
 
-    def __init__(self, m1, m2, theta, style=EUROPEAN, payoff=CALL, scheme=DOUGLAS, divs=None):
+    def __init__(self, m1, m2, theta, style=EUROPEAN, payoff=CALL, scheme=DOUGLAS, divs=None, boundary=0,
+                 dividend_schedule=0):
         if divs is not None and len(divs[0]) > 0:
             self.arrs = [np.ascontiguousarray(x, dtype=np.float64) for x in divs]
             nd = self.arrs[0].size
             self.num = Numerics(m1, m2, theta, style, payoff, scheme, nd, _d(self.arrs[0]), _d(self.arrs[1]),
-                                _d(self.arrs[2]))
+                                _d(self.arrs[2]), boundary, dividend_schedule)
         else:
             self.arrs = []
-            self.num = Numerics(m1, m2, theta, style, payoff, scheme, 0, None, None, None)
+            self.num = Numerics(m1, m2, theta, style, payoff, scheme, 0, None, None, None, boundary, dividend_schedule)
 
 
-def make_numerics(m1, m2, theta, style=EUROPEAN, payoff=CALL, scheme=DOUGLAS, divs=None):
-    return _NumKeep(m1, m2, theta, style, payoff, scheme, divs)
+def make_numerics(m1, m2, theta, style=EUROPEAN, payoff=CALL, scheme=DOUGLAS, divs=None, boundary=0,
+                  dividend_schedule=0):
+    """boundary: BC_REFERENCE_CALL (parity path) | BC_PUT; dividend_schedule: DIVIDENDS_DEVICE (parity path) |
+    DIVIDENDS_ALL — the two opt-in extensions of include/hadi.h (parity unpinned)."""
+    return _NumKeep(m1, m2, theta, style, payoff, scheme, divs, boundary, dividend_schedule)
 
 
 def grid(m1, m2, K, S0, V0):

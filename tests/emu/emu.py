@@ -15,7 +15,7 @@ _dp = C.POINTER(C.c_double)
 class Item(C.Structure):
     _fields_ = ([(k, C.c_double) for k in ("kappa", "eta", "sigma", "rho", "r_d", "r_f", "dt", "theta", "K", "ef")] +
                 [(k, C.c_int) for k in ("N", "style", "payoff", "nd", "s_off", "v_off", "e_off", "idx_s", "idx_v",
-                                        "out", "cost", "pad")])
+                                        "out", "cost", "aux", "bc", "div_all")])
 
 
 def build():

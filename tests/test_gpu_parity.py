@@ -697,3 +697,58 @@ def test_batch_update_model_equals_fresh_batch(hadi, ctx):
                 bt.update_model(hadi.make_model(**dict(BASE, r_d=0.03)))
             for x in (bt, fresh, first):
                 x.destroy()
+
+
+# ---- opt-in extensions: parity unpinned, tested against the restatement in oracle/hadi_oracle.c ----
+@pytest.mark.parametrize("m1,m2", [(50, 25), (100, 50), (64, 32)])
+def test_put_boundary_set_matches_restatement(hadi, ctx, oracle, m1, m2):
+    """HADI_BC_PUT (b1 = b2 = 0, Dirichlet K exp(-r_d tau) at s_0): full grids equal to the oracle's restatement for
+    European and American puts, with and without dividends; European puts satisfy put-call parity against the call
+    priced under the reference's boundary vectors to discretisation accuracy; Craig-Sneyd refuses the option."""
+    mdl = hadi.make_model(**BASE)
+    N = 20
+    for style in (0, 1):
+        for dv in (None, DIVS):
+            num = hadi.make_numerics(m1, m2, 0.8, style, hadi.PUT, hadi.DOUGLAS, dv, boundary=hadi.BC_PUT)
+            pts, n = hadi.make_points([93.0, 104.0], 1.0, N)
+            g = ctx.price_batch(mdl, num, pts, n, want_U=True, want_lambda=True)
+            for k, K in enumerate((93.0, 104.0)):
+                o = oracle.solve(K, N, 1.0 / N, m1=m1, m2=m2, theta=0.8, style=style, divs=dv, payoff_put=1, bc=1, **BASE)
+                assert g["prices"][k] == o["price"] and np.array_equal(g["U"][k], o["U"])
+                if style:
+                    assert np.array_equal(g["lambda"][k], o["lambda"])
+                assert g["U"][k].reshape(m2 + 1, m1 + 1)[:, 0].max() <= K   # the Dirichlet column holds K exp(-r_d T)
+    # put-call parity C - P = S0 - K exp(-r_d T) (r_f = 0), European, no dividends
+    pts, n = hadi.make_points([100.0], 1.0, 50)
+    c = ctx.price_batch(mdl, hadi.make_numerics(m1, m2, 0.8), pts, n)["prices"][0]
+    p = ctx.price_batch(mdl, hadi.make_numerics(m1, m2, 0.8, 0, hadi.PUT, hadi.DOUGLAS, None, boundary=hadi.BC_PUT), pts, n)["prices"][0]
+    assert abs((c - p) - (100.0 - 100.0 * math.exp(-0.025))) < 5e-3
+    with pytest.raises(hadi.HadiError):
+        ctx.price_batch(mdl, hadi.make_numerics(m1, m2, 0.8, 0, hadi.PUT, hadi.CRAIG_SNEYD, None, boundary=hadi.BC_PUT), pts, n)
+
+
+def test_all_dividends_schedule_matches_restatement(hadi, ctx, oracle):
+    """HADI_DIVIDENDS_ALL (the host solver's `while` schedule, src/solver.hpp:363): two dividends dated inside one step
+    are both applied — the device schedule applies one and drops the next — on split and whole solves alike."""
+    mdl = hadi.make_model(**BASE)
+    divs = ([0.2, 0.21, 0.6], [0.5, 0.3, 0.2], [0.0, 0.01, 0.02])
+    for (m1, m2) in ((50, 25), (100, 50)):
+        for style in (0, 1):
+            for sched in (hadi.DIVIDENDS_DEVICE, hadi.DIVIDENDS_ALL):
+                num = hadi.make_numerics(m1, m2, 0.8, style, hadi.CALL, hadi.DOUGLAS, divs, dividend_schedule=sched)
+                pts, n = hadi.make_points([95.0, 100.0], 1.0, 10)
+                g = ctx.price_batch(mdl, num, pts, n, want_U=True)
+                for k, K in enumerate((95.0, 100.0)):
+                    o = oracle.solve(K, 10, 0.1, m1=m1, m2=m2, theta=0.8, style=style, divs=divs, div_all=sched, **BASE)
+                    assert g["prices"][k] == o["price"] and np.array_equal(g["U"][k], o["U"])
+    # the two schedules differ on this data, and a batch beyond the persistent grid (split schedule) agrees with both
+    num_a = hadi.make_numerics(50, 25, 0.8, 1, hadi.CALL, hadi.DOUGLAS, divs, dividend_schedule=hadi.DIVIDENDS_ALL)
+    num_d = hadi.make_numerics(50, 25, 0.8, 1, hadi.CALL, hadi.DOUGLAS, divs, dividend_schedule=hadi.DIVIDENDS_DEVICE)
+    K = [80.0 + 0.05 * k for k in range(900)]
+    pts, n = hadi.make_points(K, 1.0, 10)
+    a = ctx.price_batch(mdl, num_a, pts, n)["prices"]
+    d = ctx.price_batch(mdl, num_d, pts, n)["prices"]
+    assert np.any(a != d)
+    for k in (0, 451, 899):
+        assert a[k] == oracle.solve(K[k], 10, 0.1, m1=50, m2=25, theta=0.8, style=1, divs=divs, div_all=1, want_U=False,
+                                    want_lambda=False, **BASE)["price"]

@@ -104,3 +104,24 @@ def test_lm_trajectory_small(oracle):
     a = oracle.calibrate(K, N, dt, market, **kw)
     b = oracle.calibrate(K, N, dt, market, **kw)
     assert a == b and a["iterations"] >= 1 and a["converged"] == 1
+
+
+def test_opt_in_extensions_of_the_restatement(oracle):
+    """The two extensions beyond the reference's device path (parity unpinned by construction; oracle/hadi_oracle.h):
+    the put-correct boundary set satisfies put-call parity to discretisation accuracy and leaves the parity path
+    untouched; the `while` dividend schedule applies every dividend dated inside one step."""
+    import math
+
+    kw = dict(m1=100, m2=50, theta=0.8, **BASE)
+    call = oracle.solve(100.0, 50, 1 / 50, **kw)["price"]
+    assert repr(call) == repr(oracle.solve(100.0, 50, 1 / 50, bc=0, div_all=0, **kw)["price"])
+    put = oracle.solve(100.0, 50, 1 / 50, payoff_put=1, bc=1, **kw)
+    assert abs((call - put["price"]) - (100.0 - 100.0 * math.exp(-0.025))) < 5e-3
+    col0 = put["U"].reshape(51, 101)[:, 0]
+    assert np.all(col0 == 100.0 * math.exp(-0.025 * (1 / 50) * 50))
+    am = oracle.solve(100.0, 50, 1 / 50, payoff_put=1, bc=1, style=1, **kw)["price"]
+    assert am > put["price"]
+    divs = ([0.2, 0.21, 0.6], [0.5, 0.3, 0.2], [0.0, 0.0, 0.0])
+    dev = oracle.solve(100.0, 10, 0.1, divs=divs, **kw)["price"]
+    allp = oracle.solve(100.0, 10, 0.1, divs=divs, div_all=1, **kw)["price"]
+    assert allp < dev    # the second dividend of the step (0.3 at t = 0.21) is dropped by the device schedule
