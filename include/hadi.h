@@ -61,6 +61,10 @@ extern "C" {
 #define HADI_PUT 1               /* put PAYOFF under the reference's call boundary vectors */
 #define HADI_DOUGLAS 0
 #define HADI_CRAIG_SNEYD 1
+#define HADI_MODIFIED_CRAIG_SNEYD 2   /* MCS_scheme_shuffled AS SHIPPED (src/solver.hpp:917-1075; the reference marks it as not
+                                         working and it is not a usable pricer: 3.76 where the other schemes give 8.87) —
+                                         reproduced bit for bit, for callers that depend on the reference's numbers */
+#define HADI_HUNDSDORFER_VERWER 3     /* extension, not in the reference (parity unpinned): second order in time for any theta */
 /* opt-in extensions beyond the reference's device path.  PARITY UNPINNED: the reference
  * has no such code path; the CPU restatement in oracle/hadi_oracle.c is the definition the GPU path is tested against. */
 #define HADI_BC_REFERENCE_CALL 0   /* the reference's boundary vectors b1, b2 (call asymptotics; src/BoundaryConditions.hpp:7-12) */
@@ -96,7 +100,8 @@ typedef struct {
   double theta;
   int style;        /* HADI_EUROPEAN | HADI_AMERICAN */
   int payoff;       /* HADI_CALL | HADI_PUT */
-  int scheme;       /* HADI_DOUGLAS (device path of the reference) | HADI_CRAIG_SNEYD */
+  int scheme;       /* HADI_DOUGLAS (device path of the reference) | HADI_CRAIG_SNEYD | HADI_MODIFIED_CRAIG_SNEYD |
+                       HADI_HUNDSDORFER_VERWER (the last three: European, no dividends, reference call boundary vectors) */
   int num_dividends;
   const double* dividend_dates;
   const double* dividend_amounts;
@@ -310,6 +315,17 @@ int hadi_write_calibration_csv(const char* path, int format, double spot, double
                                int num_strikes, const hadi_point* points, const double* market,
                                const double* fitted, const hadi_model* initial, const hadi_lm_result* result,
                                double total_time_s, double iv_epsilon);
+
+/* ---- convergence-study harness (src/solver.cpp:50-295) ---------------------------- */
+/* ConvergenceExporter::testWithRelatedGridSizes: one call (strike K, maturity T) priced on the grids m1 = 2*m2 for every
+ * m2 of the list with N steps of `scheme`; relative error against ref_price, mean wall seconds of `repeats` solves
+ * (the reference uses N = 20, theta = 0.8, 20 repeats).  Output arrays have n_sizes entries; any may be NULL. */
+int hadi_convergence_study(hadi_ctx* ctx, const hadi_model* model, double K, double T, int N, double theta, int scheme,
+                           int n_sizes, const int* m2_sizes, double ref_price, int repeats, double* prices,
+                           double* rel_errors, double* seconds);
+/* ConvergenceExporter::exportToCSV: header m1,m2,price,error,time; scientific notation, ten digits */
+int hadi_write_convergence_csv(const char* path, int n_sizes, const int* m2_sizes, const double* prices,
+                               const double* rel_errors, const double* seconds);
 
 #ifdef __cplusplus
 }

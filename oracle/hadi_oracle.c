@@ -482,6 +482,79 @@ static void craig_sneyd(ho_ws *w, const ho_numerics *num, int N, double dt, doub
   free(Y2); free(A0Y2); free(Y0t); free(Y1t);
 }
 
+
+/* src/solver.hpp:917-1075, MCS_scheme_shuffled as shipped: the corrector starts from Y_0 AFTER it was overwritten with
+ * the right-hand side of the first A1 solve (":968 Reuse Y_0 to store RHS"), and takes A1 U, A2 U in its two implicit
+ * stages.  European only, host matrix classes and boundary vectors. */
+static void modified_craig_sneyd(ho_ws *w, const ho_numerics *num, int N, double dt, double r_f, double *U) {
+  const int P = w->P;
+  const double theta = num->theta;
+  double *Y2 = dalloc(P), *A0Y2 = dalloc(P), *A1Y2 = dalloc(P), *A2Y2 = dalloc(P), *Yt = dalloc(P), *prev = dalloc(P);
+  for (int n = 1; n <= N; ++n) {
+    const double e1 = exp(r_f * dt * n), e0 = exp(r_f * dt * (n - 1));
+    mul_a0(w, U, w->R0);
+    mul_a1_host(w, U, w->R1);
+    mul_a2(w, U, w->R2);
+    for (int p = 0; p < P; ++p) {
+      prev[p] = w->R0[p] + w->R1[p] + w->R2[p] + w->b[p] * e0;
+      w->Y0[p] = U[p] + dt * prev[p];
+    }
+    for (int p = 0; p < P; ++p) w->Y0[p] = w->Y0[p] + theta * dt * (w->b1[p] * e1 - (w->R1[p] + w->b1[p] * e0));
+    solve_a1(w, w->Y1, w->Y0);
+    for (int p = 0; p < P; ++p) w->Y1[p] = w->Y1[p] + theta * dt * (w->b2[p] * e1 - (w->R2[p] + w->b2[p] * e0));
+    solve_a2(w, Y2, w->Y1);
+    mul_a0(w, Y2, A0Y2);
+    mul_a1_host(w, Y2, A1Y2);
+    mul_a2(w, Y2, A2Y2);
+    for (int p = 0; p < P; ++p) {
+      const double F0_n = A0Y2[p] + 0.0 * e1, F0_nm1 = w->R0[p] + 0.0 * e0;   /* b0 == 0 */
+      const double y0_hat = w->Y0[p] + theta * dt * (F0_n - F0_nm1);
+      const double curr = A0Y2[p] + A1Y2[p] + A2Y2[p] + w->b[p] * e1;
+      Yt[p] = y0_hat + (0.5 - theta) * dt * (curr - prev[p]);
+    }
+    for (int p = 0; p < P; ++p) Yt[p] = Yt[p] + theta * dt * (w->b1[p] * e1 - (w->R1[p] + w->b1[p] * e0));
+    solve_a1(w, w->Y1, Yt);
+    for (int p = 0; p < P; ++p) w->Y1[p] = w->Y1[p] + theta * dt * (w->b2[p] * e1 - (w->R2[p] + w->b2[p] * e0));
+    solve_a2(w, U, w->Y1);
+  }
+  free(Y2); free(A0Y2); free(A1Y2); free(A2Y2); free(Yt); free(prev);
+}
+
+/* Hundsdorfer-Verwer (extension; in 't Hout & Foulon 2010, scheme (2.6)), on the same operators and boundary vectors:
+ *   Y0 = U + dt F(U);  Yj = Y(j-1) + theta dt (Fj(Yj) - Fj(U)), j = 1, 2;
+ *   Y0~ = Y0 + 1/2 dt (F(Y2) - F(U));  Yj~ = Y(j-1)~ + theta dt (Fj(Yj~) - Fj(Y2)), j = 1, 2;  U <- Y2~.
+ * F(X) = A0 X + A1 X + A2 X + b e,  Fj(X) = Aj X + bj e; the explicit parts are summed left to right. */
+static void hundsdorfer_verwer(ho_ws *w, const ho_numerics *num, int N, double dt, double r_f, double *U) {
+  const int P = w->P;
+  const double theta = num->theta;
+  double *Y2 = dalloc(P), *A0Y2 = dalloc(P), *A1Y2 = dalloc(P), *A2Y2 = dalloc(P), *Yt = dalloc(P);
+  for (int n = 1; n <= N; ++n) {
+    const double e1 = exp(r_f * dt * n), e0 = exp(r_f * dt * (n - 1));
+    mul_a0(w, U, w->R0);
+    mul_a1_host(w, U, w->R1);
+    mul_a2(w, U, w->R2);
+    for (int p = 0; p < P; ++p) w->Y0[p] = U[p] + dt * (w->R0[p] + w->R1[p] + w->R2[p] + w->b[p] * e0);
+    for (int p = 0; p < P; ++p) w->Y1[p] = w->Y0[p] + theta * dt * (w->b1[p] * e1 - (w->R1[p] + w->b1[p] * e0));
+    solve_a1(w, w->Y1, w->Y1);
+    for (int p = 0; p < P; ++p) Y2[p] = w->Y1[p] + theta * dt * (w->b2[p] * e1 - (w->R2[p] + w->b2[p] * e0));
+    solve_a2(w, Y2, Y2);
+    mul_a0(w, Y2, A0Y2);
+    mul_a1_host(w, Y2, A1Y2);
+    mul_a2(w, Y2, A2Y2);
+    for (int p = 0; p < P; ++p) {
+      const double curr = A0Y2[p] + A1Y2[p] + A2Y2[p] + w->b[p] * e1;
+      const double prev = w->R0[p] + w->R1[p] + w->R2[p] + w->b[p] * e0;
+      Yt[p] = w->Y0[p] + 0.5 * dt * (curr - prev);
+    }
+    /* the implicit stages of the corrector are centred on Y2: (I - theta dt A1) Y1~ = Y0~ - theta dt A1 Y2 (b1 terms cancel) */
+    for (int p = 0; p < P; ++p) Yt[p] = Yt[p] + theta * dt * (w->b1[p] * e1 - (A1Y2[p] + w->b1[p] * e1));
+    solve_a1(w, Yt, Yt);
+    for (int p = 0; p < P; ++p) U[p] = Yt[p] + theta * dt * (w->b2[p] * e1 - (A2Y2[p] + w->b2[p] * e1));
+    solve_a2(w, U, U);
+  }
+  free(Y2); free(A0Y2); free(A1Y2); free(A2Y2); free(Yt);
+}
+
 /* ------------------------------------------------------------------ one solve */
 
 static void setup_option(ho_ws *w, const ho_model *mdl, const ho_numerics *num, double K, double V0_grid) {
@@ -504,6 +577,10 @@ static int solve_ws(ho_ws *w, const ho_model *mdl, const ho_numerics *num, int N
   memcpy(U, w->U0, sizeof(double) * (size_t)w->P);
   if (num->scheme == 1)
     craig_sneyd(w, num, N, dt, mdl->r_f, U);
+  else if (num->scheme == 2)
+    modified_craig_sneyd(w, num, N, dt, mdl->r_f, U);
+  else if (num->scheme == 3)
+    hundsdorfer_verwer(w, num, N, dt, mdl->r_f, U);
   else
     douglas(w, num, N, dt, mdl->r_f, mdl->r_d, K, U);
   return 0;
@@ -525,7 +602,7 @@ int ho_solve(const ho_model *mdl, const ho_numerics *num, double K, int N, doubl
   ho_ws *w = ws_new(num->m1, num->m2);
   double *U = dalloc(w->P);
   setup_option(w, mdl, num, K, V0_for_grid);
-  build_bounds(w, mdl->r_d, mdl->r_f, N, dt, num->scheme == 1, num->bc);
+  build_bounds(w, mdl->r_d, mdl->r_f, N, dt, num->scheme >= 1, num->bc);
   build_all(w, mdl, num, dt);
   solve_ws(w, mdl, num, N, dt, K, U);
   const int rc = pick(w, mdl->S0, V0_for_grid, U, price);
@@ -557,7 +634,7 @@ int ho_jacobian_batch(const ho_model *mdl, const ho_numerics *num, int n, const 
     const int N = Ns[k];
     const double dt = dts[k];
     setup_option(w, mdl, num, strikes[k], mdl->V0);
-    build_bounds(w, mdl->r_d, mdl->r_f, N, dt, num->scheme == 1, num->bc);
+    build_bounds(w, mdl->r_d, mdl->r_f, N, dt, num->scheme >= 1, num->bc);
     build_all(w, mdl, num, dt);
     solve_ws(w, mdl, num, N, dt, strikes[k], U);
     double base_price = 0.0;

@@ -26,7 +26,9 @@ typedef struct {
   double theta;                         /* ADI theta */
   int style;                            /* 0 European, 1 American (Ikonen-Toivanen) */
   int payoff_put;                       /* 0: max(s-K,0)  1: max(K-s,0) (reference call BCs) */
-  int scheme;                           /* 0 Douglas (device path), 1 Craig-Sneyd (host path) */
+  int scheme;                           /* 0 Douglas (device path), 1 Craig-Sneyd (host path), 2 Modified Craig-Sneyd
+                                           as the reference ships it (src/solver.hpp:917-1075, pinned to oracle/_ref),
+                                           3 Hundsdorfer-Verwer (extension, not in the reference: parity unpinned) */
   int nd;                               /* number of dividends */
   const double *div_dates, *div_amounts, *div_pcts;
   /* opt-in extensions beyond the reference's device path (PARITY UNPINNED: the

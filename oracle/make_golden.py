@@ -180,6 +180,13 @@ def more_fixtures():
         market_sha256=digest(market),
         survey="18 iterations, kappa=0.52875 eta=0.114716 sigma=0.0901574 rho=0.120892 v0=0.0800021 err=0.19322")
     json.dump(out, open(os.path.join(OUT, "lm_more.json"), "w"), indent=0)
+    # ---- Modified Craig-Sneyd as the reference ships it (src/solver.hpp:917-1075): price and digest of the full grid
+    Rs = RefLib()
+    mcs = []
+    for (m1, m2, N) in [(50, 25, 20), (100, 50, 20), (64, 32, 9)]:
+        price, U = Rs.host_scheme(2, K=100.0, T=1.0, m1=m1, m2=m2, N=N, want_U=True, **BASE)
+        mcs.append(dict(m1=m1, m2=m2, N=N, K=100.0, T=1.0, price=repr(float(price)), U_sha256=digest(U)))
+    json.dump(dict(base=BASE, cases=mcs), open(os.path.join(OUT, "mcs.json"), "w"), indent=0)
     for k, v in out.items():
         print(k, v["iterations"], v["converged"], v["params"], v["final_error"], v["pde_solves"])
 

@@ -446,6 +446,9 @@ int hadi_ref_host_scheme(int scheme, double K, double S_0, double V_0, double T,
   if (scheme == 0)
     DO_scheme_shuffle<Kokkos::View<double*>>(m, m1, m2, N, U_0, delta_t, theta, A0, A1, A2_shuf,
                                               bounds, r_f, U);
+  else if (scheme == 2)   // Modified Craig-Sneyd as the reference ships it (src/solver.hpp:917-1075)
+    MCS_scheme_shuffled<Kokkos::View<double*>>(m, m1, m2, N, U_0, delta_t, theta, A0, A1, A2_shuf,
+                                                bounds, r_f, U);
   else
     CS_scheme_shuffled<Kokkos::View<double*>>(m, m1, m2, N, U_0, delta_t, theta, A0, A1, A2_shuf,
                                                bounds, r_f, U);

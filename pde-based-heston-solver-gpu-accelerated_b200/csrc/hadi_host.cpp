@@ -255,7 +255,7 @@ bool valid_numerics(const hadi_numerics* num) {
     return false;
   // opt-in extensions (parity unpinned): the reference defines Craig-Sneyd with its call boundary vectors only
   if (num->boundary != HADI_BC_REFERENCE_CALL && num->boundary != HADI_BC_PUT) return false;
-  if (num->boundary == HADI_BC_PUT && num->scheme == HADI_CRAIG_SNEYD) return false;
+  if (num->boundary == HADI_BC_PUT && num->scheme != HADI_DOUGLAS) return false;
   if (num->dividend_schedule != HADI_DIVIDENDS_DEVICE && num->dividend_schedule != HADI_DIVIDENDS_ALL) return false;
   return true;
 }
@@ -608,9 +608,11 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
   if (!valid_mode(mode)) return fail(ctx, HADI_ERR_ARG, "bad mode");
   if (mode == HADI_MODE_JACOBIAN_CENTRAL && !(model->V0 - eps5[4] > 0.0))
     return fail(ctx, HADI_ERR_ARG, "central differences need V0 - eps > 0");
-  if (num->scheme != HADI_DOUGLAS && num->scheme != HADI_CRAIG_SNEYD) return fail(ctx, HADI_ERR_ARG, "unknown scheme");
+  if (num->scheme != HADI_DOUGLAS && num->scheme != HADI_CRAIG_SNEYD && num->scheme != HADI_MODIFIED_CRAIG_SNEYD &&
+      num->scheme != HADI_HUNDSDORFER_VERWER)
+    return fail(ctx, HADI_ERR_ARG, "unknown scheme");
   // the reference defines Craig-Sneyd for European options without dividends only (src/solver.hpp:781)
-  if (num->scheme == HADI_CRAIG_SNEYD && (num->style != HADI_EUROPEAN || num->num_dividends > 0))
+  if (num->scheme != HADI_DOUGLAS && (num->style != HADI_EUROPEAN || num->num_dividends > 0))
     return fail(ctx, HADI_ERR_ARG, "Craig-Sneyd: European options without dividends only");
   const int nc = n_columns(mode);
   const int total_items = n * nc;
@@ -632,7 +634,7 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
   if (plan_hit != ctx->plans.end() && plan_hit->second.first == 0) {
     plan = plan_hit->second.second;
   } else {
-    const bool cs = num->scheme == HADI_CRAIG_SNEYD;
+    const bool cs = num->scheme != HADI_DOUGLAS;   // the Craig-Sneyd family runs on the global-state kernels
     // few large solves: spread each over a thread-block cluster (needs the global working set; the dividend
     // jump keeps per-CTA tables and stays on the one-CTA-per-solve kernels)
     const int n_it = (item_end < 0 ? n * n_columns(mode) : item_end) - item_begin;
@@ -833,7 +835,7 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
   if (plan.cluster > 1) b->grid_ctas = plan.cluster * std::max(1, std::min(n_items, plan.sm_count / plan.cluster));
   if (const char* cap = getenv("HADI_MAX_CTAS"))  // development aid: cap the persistent grid
     if (atoi(cap) > 0) b->grid_ctas = std::min(b->grid_ctas, atoi(cap));
-  const size_t stride = hadi_scratch_layout(m1, m2, g.ld, g.pj, plan.global_state, num->scheme == HADI_CRAIG_SNEYD).total;
+  const size_t stride = hadi_scratch_layout(m1, m2, g.ld, g.pj, plan.global_state, num->scheme != HADI_DOUGLAS).total;
   double* d_scratch = (double*)take(sizeof(double) * stride * (size_t)(b->grid_ctas / std::max(1, plan.cluster)), false);
   if (!h_stage || !d_stage || !b->h_values || !d_values || !d_counter || !d_scratch) {
     release_all();

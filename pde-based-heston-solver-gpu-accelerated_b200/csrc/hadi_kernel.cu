@@ -401,7 +401,7 @@ __device__ __forceinline__ bool hadi_solve_item_cs(const HadiLaunch& L, const Ha
   if (tid <= m2) feed.begin_item(2 * it.N, tid);
   for (int n = 1; n <= it.N; ++n) {
     const double e0 = eg[n - 1], e1 = eg[n];
-    hadi_cs_predict(it, w, cs, e0, e1, tid, NT);
+    hadi_cs_predict(it, w, cs, e0, e1, tid, NT, L.scheme);
     HADI_SYNC();
     hadi_phase_solve_a1<0, 0, EXACT>(it, w, e0, e1, 2 * n - 1, tid, NT, feed, bad, nullptr, 2 * it.N);
     HADI_SYNC();
@@ -409,11 +409,12 @@ __device__ __forceinline__ bool hadi_solve_item_cs(const HadiLaunch& L, const Ha
     HADI_SYNC();
     hadi_phase_solve_a2<0, 0, EXACT>(it, w, tid, NT, bad);   // Y2 -> U
     HADI_SYNC();
-    hadi_cs_correct(it, w, cs, e0, e1, tid, NT);
+    if (L.scheme == HADI_SCHEME_CS) hadi_cs_correct(it, w, cs, e0, e1, tid, NT);
+    else hadi_cs_correct2(it, w, cs, e0, e1, tid, NT, L.scheme);
     HADI_SYNC();
     hadi_phase_solve_a1<0, 0, EXACT>(it, w, e0, e1, 2 * n, tid, NT, feed, bad, nullptr, 2 * it.N);
     HADI_SYNC();
-    hadi_cs_rhs2(it, w, cs, e0, e1, tid, NT);
+    hadi_cs_rhs2(it, w, cs, L.scheme == HADI_SCHEME_HV ? e1 : e0, e1, tid, NT);
     HADI_SYNC();
     hadi_phase_solve_a2<0, 0, EXACT>(it, w, tid, NT, bad);
     HADI_SYNC();
@@ -460,7 +461,7 @@ __global__ void __launch_bounds__(NT * DUO, MINB) hadi_douglas_kernel(const Hadi
     w.stg = reinterpret_cast<double*>(sbase + lay.ring);
   }
   double* scratch = L.scratch + (size_t)(vb < vgrid ? vb : 0) * L.scratch_stride;
-  const HadiScratchLayout gl = hadi_scratch_layout(m1, m2, w.ld, w.pj, GLOBAL, GLOBAL && L.scheme == 1);
+  const HadiScratchLayout gl = hadi_scratch_layout(m1, m2, w.ld, w.pj, GLOBAL, GLOBAL && L.scheme >= 1);
   // the working set: shared memory, or (GLOBAL) L2-resident global scratch for grids beyond it
   double* Ualloc = GLOBAL ? scratch + gl.U : reinterpret_cast<double*>(sbase + lay.U);
   w.U = Ualloc + HADI_HALO * w.ld + 1;
@@ -587,7 +588,7 @@ __global__ void __launch_bounds__(NT * DUO, MINB) hadi_douglas_kernel(const Hadi
     // item is re-solved with IEEE divisions so that the published value is exact in every case
     bool cs_done = false;
     if constexpr (GLOBAL) {
-      if (L.scheme == 1) {
+      if (L.scheme >= 1) {
         if (hadi_solve_item_cs<NT, false>(L, it, w, cs, feed, tid, bar)) hadi_solve_item_cs<NT, true>(L, it, w, cs, feed, tid, bar);
         cs_done = true;
       }
@@ -716,8 +717,8 @@ __device__ __forceinline__ bool hadi_cluster_solve(const HadiLaunch& L, const Ha
   hadi_csync();
   for (int n = 1; n <= it.N; ++n) {
     const double e0 = eg[n - 1], e1 = eg[n];
-    if (L.scheme == 1) {
-      hadi_cs_predict(it, w, cs, e0, e1, gtid, gnt);
+    if (L.scheme >= 1) {
+      hadi_cs_predict(it, w, cs, e0, e1, gtid, gnt, L.scheme);
       hadi_csync();
       hadi_phase_solve_a1<0, 0, EXACT>(it, w, e0, e1, 2 * n - 1, tid, NT, feed, bad, nullptr, 2 * it.N);
       hadi_csync();
@@ -725,11 +726,12 @@ __device__ __forceinline__ bool hadi_cluster_solve(const HadiLaunch& L, const Ha
       hadi_csync();
       hadi_phase_solve_a2<0, 0, EXACT>(it, w, tid, NT, bad);
       hadi_csync();
-      hadi_cs_correct(it, w, cs, e0, e1, gtid, gnt);
+      if (L.scheme == HADI_SCHEME_CS) hadi_cs_correct(it, w, cs, e0, e1, gtid, gnt);
+      else hadi_cs_correct2(it, w, cs, e0, e1, gtid, gnt, L.scheme);
       hadi_csync();
       hadi_phase_solve_a1<0, 0, EXACT>(it, w, e0, e1, 2 * n, tid, NT, feed, bad, nullptr, 2 * it.N);
       hadi_csync();
-      hadi_cs_rhs2(it, w, cs, e0, e1, gtid, gnt);
+      hadi_cs_rhs2(it, w, cs, L.scheme == HADI_SCHEME_HV ? e1 : e0, e1, gtid, gnt);
       hadi_csync();
       hadi_phase_solve_a2<0, 0, EXACT>(it, w, tid, NT, bad);
       hadi_csync();
@@ -773,7 +775,7 @@ __global__ void __cluster_dims__(HADI_CLUSTER, 1, 1) __launch_bounds__(NT, 1) ha
   const HadiSmemLayout lay = hadi_smem_layout(m1, m2, w.ld, w.n1, w.n2, w.pj, false, true);
   char* sbase = reinterpret_cast<char*>(smem);
   double* scratch = L.scratch + (size_t)cid * L.scratch_stride;
-  const HadiScratchLayout gl = hadi_scratch_layout(m1, m2, w.ld, w.pj, true, L.scheme == 1);
+  const HadiScratchLayout gl = hadi_scratch_layout(m1, m2, w.ld, w.pj, true, L.scheme >= 1);
   double* Ualloc = scratch + gl.U;
   w.U = Ualloc + HADI_HALO * w.ld + 1;
   w.Y = scratch + gl.Y;

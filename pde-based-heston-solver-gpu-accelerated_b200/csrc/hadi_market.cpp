@@ -7,8 +7,10 @@
 //                                                                    1498-1584, 2853-2923
 // The reference streams doubles with operator<< at the default precision; the writers below do the same,
 // so that for equal numbers the files are equal byte for byte (the Time= field aside).
+#include <chrono>
 #include <cmath>
 #include <fstream>
+#include <iomanip>
 #include <string>
 #include <vector>
 
@@ -186,6 +188,51 @@ int hadi_write_calibration_csv(const char* path, int format, double spot, double
   }
   out.close();
   return out.fail() ? HADI_ERR_ARG : HADI_OK;
+}
+
+
+// ---- convergence-study harness ---------------------------------------------------
+// ConvergenceExporter::testWithRelatedGridSizes (src/solver.cpp:61-150): one call priced on the grids m1 = 2 m2 for
+// every m2 of the list, N time steps, relative error against a reference price, mean wall time of `repeats` solves
+// (the reference: N = 20, theta = 0.8, 20 repeats) — here with any stepping scheme of the library and every solve on
+// the GPU.  prices / rel_errors / seconds have n_sizes entries; any of them may be NULL.
+int hadi_convergence_study(hadi_ctx* ctx, const hadi_model* model, double K, double T, int N, double theta, int scheme,
+                           int n_sizes, const int* m2_sizes, double ref_price, int repeats, double* prices,
+                           double* rel_errors, double* seconds) {
+  if (!ctx || !model || !m2_sizes || n_sizes < 0 || N < 1 || !(T > 0) || repeats < 1) return HADI_ERR_ARG;
+  for (int k = 0; k < n_sizes; ++k) {
+    const int m2 = m2_sizes[k], m1 = 2 * m2;
+    hadi_numerics num{};
+    num.m1 = m1; num.m2 = m2; num.theta = theta;
+    num.style = HADI_EUROPEAN; num.payoff = HADI_CALL; num.scheme = scheme;
+    const hadi_point pt{K, T, N, T / N, 0};
+    double price = 0.0, total = 0.0;
+    for (int r = 0; r < repeats; ++r) {
+      const auto t0 = std::chrono::steady_clock::now();
+      const int rc = hadi_price_batch(ctx, model, &num, 1, &pt, &price, nullptr, nullptr);
+      if (rc != HADI_OK) return rc;
+      total += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    if (prices) prices[k] = price;
+    if (rel_errors) rel_errors[k] = std::abs(price - ref_price) / ref_price;
+    if (seconds) seconds[k] = total / repeats;
+  }
+  return HADI_OK;
+}
+
+// ConvergenceExporter::exportToCSV (src/solver.cpp:281-295): <name>_convergence.csv, header m1,m2,price,error,time,
+// numbers in scientific notation with ten digits (the stream state the reference leaves set after the first price).
+int hadi_write_convergence_csv(const char* path, int n_sizes, const int* m2_sizes, const double* prices,
+                               const double* rel_errors, const double* seconds) {
+  if (!path || n_sizes < 0 || (n_sizes > 0 && (!m2_sizes || !prices || !rel_errors || !seconds))) return HADI_ERR_ARG;
+  std::ofstream file(path);
+  if (!file) return HADI_ERR_ARG;
+  file << "m1,m2,price,error,time\n";
+  for (int i = 0; i < n_sizes; ++i) {
+    file << 2 * m2_sizes[i] << "," << m2_sizes[i] << "," << std::scientific << std::setprecision(10) << prices[i] << ","
+         << rel_errors[i] << "," << seconds[i] << "\n";
+  }
+  return file.good() ? HADI_OK : HADI_ERR_ARG;
 }
 
 }  // extern "C"

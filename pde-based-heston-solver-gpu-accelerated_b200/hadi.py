@@ -20,7 +20,7 @@ _ip = C.POINTER(C.c_int)
 OK, ERR_ARG, ERR_GRID, ERR_CUDA, ERR_SMEM, ERR_COMM, ERR_NOMEM = 0, -1, -2, -3, -4, -5, -6
 EUROPEAN, AMERICAN = 0, 1
 CALL, PUT = 0, 1
-DOUGLAS, CRAIG_SNEYD = 0, 1
+DOUGLAS, CRAIG_SNEYD, MODIFIED_CRAIG_SNEYD, HUNDSDORFER_VERWER = 0, 1, 2, 3
 BC_REFERENCE_CALL, BC_PUT = 0, 1
 DIVIDENDS_DEVICE, DIVIDENDS_ALL = 0, 1
 MODE_PRICE, MODE_JACOBIAN, MODE_JACOBIAN_INTERP, MODE_JACOBIAN_CENTRAL = 0, 1, 2, 3
@@ -125,6 +125,9 @@ def lib():
         L.hadi_jacobian_batch_sharded.argtypes = [C.c_void_p, C.POINTER(Model), C.POINTER(Numerics), C.c_int,
                                                   C.POINTER(Point), C.POINTER(JacobianOptions), _dp, _dp]
         L.hadi_batch_update_model.argtypes = [C.c_void_p, C.POINTER(Model)]
+        L.hadi_convergence_study.argtypes = [C.c_void_p, C.POINTER(Model), C.c_double, C.c_double, C.c_int, C.c_double,
+                                             C.c_int, C.c_int, C.POINTER(C.c_int), C.c_double, C.c_int, _dp, _dp, _dp]
+        L.hadi_write_convergence_csv.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int), _dp, _dp, _dp]
         L.hadi_exact_reruns.argtypes = [C.c_void_p]
         L.hadi_exact_reruns.restype = C.c_longlong
         L.hadi_batch_exact_reruns.argtypes = [C.c_void_p]
@@ -325,6 +328,16 @@ def write_calibration_csv(path, fmt, spot, r_d, n_maturities, n_strikes, pts, ma
         raise HadiError(rc)
 
 
+def write_convergence_csv(path, m2_sizes, prices, errors, seconds):
+    m2s = np.ascontiguousarray(m2_sizes, dtype=np.int32)
+    rc = lib().hadi_write_convergence_csv(str(path).encode(), m2s.size, m2s.ctypes.data_as(C.POINTER(C.c_int)),
+                                          _d(np.ascontiguousarray(prices, dtype=np.float64)),
+                                          _d(np.ascontiguousarray(errors, dtype=np.float64)),
+                                          _d(np.ascontiguousarray(seconds, dtype=np.float64)))
+    if rc != OK:
+        raise HadiError(rc, "hadi_write_convergence_csv")
+
+
 def solve5(A, b):
     A = np.ascontiguousarray(A, dtype=np.float64)
     b = np.ascontiguousarray(b, dtype=np.float64)
@@ -461,6 +474,16 @@ class Context:
         self._check(lib().hadi_jacobian_batch_sharded(self._h, C.byref(model), C.byref(num.num), n, pts, C.byref(jo),
                                                       _d(J), _d(base)))
         return J[:n], base[:n]
+
+    def convergence_study(self, model, K, T, N, theta, scheme, m2_sizes, ref_price, repeats=20):
+        """ConvergenceExporter::testWithRelatedGridSizes on the GPU: (prices, relative errors, mean seconds)."""
+        m2s = np.ascontiguousarray(m2_sizes, dtype=np.int32)
+        n = m2s.size
+        p, e, t = np.zeros(max(n, 1)), np.zeros(max(n, 1)), np.zeros(max(n, 1))
+        self._check(lib().hadi_convergence_study(self._h, C.byref(model), K, T, N, theta, scheme, n,
+                                                 m2s.ctypes.data_as(C.POINTER(C.c_int)), ref_price, repeats, _d(p), _d(e),
+                                                 _d(t)))
+        return p[:n], e[:n], t[:n]
 
     @property
     def exact_reruns(self):

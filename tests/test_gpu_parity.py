@@ -752,3 +752,53 @@ def test_all_dividends_schedule_matches_restatement(hadi, ctx, oracle):
     for k in (0, 451, 899):
         assert a[k] == oracle.solve(K[k], 10, 0.1, m1=50, m2=25, theta=0.8, style=1, divs=divs, div_all=1, want_U=False,
                                     want_lambda=False, **BASE)["price"]
+
+
+# ---- neighbouring splitting schemes and the convergence-study harness ------------------------------
+def test_modified_craig_sneyd_and_hundsdorfer_verwer(hadi, ctx, oracle, monkeypatch):
+    """Scheme 2 = the reference's shipped MCS (pinned: tests/golden/mcs.json from oracle/_ref), scheme 3 = Hundsdorfer-
+    Verwer (extension; against the restatement): full grids bit-equal on the one-CTA global-state kernel and on the
+    thread-block-cluster kernel; American items and dividends are refused as for Craig-Sneyd."""
+    mdl = hadi.make_model(**BASE)
+    G = golden("mcs.json")
+    for c in G["cases"]:
+        for variant in (None, "7"):
+            if variant:
+                monkeypatch.setenv("HADI_FORCE_VARIANT", variant)
+            num = hadi.make_numerics(c["m1"], c["m2"], 0.8, hadi.EUROPEAN, hadi.CALL, hadi.MODIFIED_CRAIG_SNEYD)
+            pts, n = hadi.make_points([c["K"]], c["T"], c["N"])
+            g = ctx.price_batch(mdl, num, pts, n, want_U=True)
+            assert repr(float(g["prices"][0])) == c["price"] and digest(g["U"][0]) == c["U_sha256"]
+            numh = hadi.make_numerics(c["m1"], c["m2"], 0.8, hadi.EUROPEAN, hadi.CALL, hadi.HUNDSDORFER_VERWER)
+            h = ctx.price_batch(mdl, numh, pts, n, want_U=True)
+            o = oracle.solve(c["K"], c["N"], c["T"] / c["N"], m1=c["m1"], m2=c["m2"], theta=0.8, scheme=3,
+                             want_lambda=False, **BASE)
+            assert h["prices"][0] == o["price"] and np.array_equal(h["U"][0], o["U"])
+            monkeypatch.delenv("HADI_FORCE_VARIANT", raising=False)
+    pts, n = hadi.make_points([100.0], 1.0, 10)
+    for scheme in (hadi.MODIFIED_CRAIG_SNEYD, hadi.HUNDSDORFER_VERWER):
+        with pytest.raises(hadi.HadiError):
+            ctx.price_batch(mdl, hadi.make_numerics(50, 25, 0.8, hadi.AMERICAN, hadi.CALL, scheme), pts, n)
+        with pytest.raises(hadi.HadiError):
+            ctx.price_batch(mdl, hadi.make_numerics(50, 25, 0.8, hadi.EUROPEAN, hadi.CALL, scheme, DIVS), pts, n)
+
+
+def test_convergence_study_harness(hadi, ctx, oracle, tmp_path):
+    """hadi_convergence_study / hadi_write_convergence_csv (ConvergenceExporter, src/solver.cpp:50-295): grids m1 = 2*m2,
+    N = 20, theta = 0.8; prices are the stand-alone solves' bit for bit, the error falls as the grid is refined, and the
+    CSV has the reference's header and number format."""
+    mdl = hadi.make_model(**BASE)
+    ref_price = 8.8948693600540167          # src/solver.cpp:1666
+    sizes = [15, 25, 50, 75]
+    for scheme in (hadi.DOUGLAS, hadi.CRAIG_SNEYD, hadi.HUNDSDORFER_VERWER):
+        p, e, t = ctx.convergence_study(mdl, 100.0, 1.0, 20, 0.8, scheme, sizes, ref_price, repeats=2)
+        for k, m2 in enumerate(sizes[:3]):
+            o = oracle.solve(100.0, 20, 1.0 / 20, m1=2 * m2, m2=m2, theta=0.8, scheme=scheme, want_U=False,
+                             want_lambda=False, **BASE)["price"]
+            assert p[k] == o and e[k] == abs(o - ref_price) / ref_price
+        assert e[0] > e[2] and np.all(t > 0)
+    path = tmp_path / "study_convergence.csv"
+    hadi.write_convergence_csv(path, sizes, p, e, t)
+    lines = open(path).read().splitlines()
+    assert lines[0] == "m1,m2,price,error,time" and len(lines) == 1 + len(sizes)
+    assert lines[1] == "30,15,%.10e,%.10e,%.10e" % (p[0], e[0], t[0])

@@ -125,3 +125,27 @@ def test_opt_in_extensions_of_the_restatement(oracle):
     dev = oracle.solve(100.0, 10, 0.1, divs=divs, **kw)["price"]
     allp = oracle.solve(100.0, 10, 0.1, divs=divs, div_all=1, **kw)["price"]
     assert allp < dev    # the second dividend of the step (0.3 at t = 0.21) is dropped by the device schedule
+
+
+def test_modified_craig_sneyd_restatement_equals_the_shipped_scheme(oracle):
+    """Scheme 2 restates MCS_scheme_shuffled exactly as the reference ships it (src/solver.hpp:917-1075) — including the
+    overwritten Y_0 that makes it a non-working pricer — and is pinned to oracle/_ref (tests/golden/mcs.json)."""
+    G = golden("mcs.json")
+    for c in G["cases"]:
+        b = dict(G["base"])
+        o = oracle.solve(c["K"], c["N"], c["T"] / c["N"], m1=c["m1"], m2=c["m2"], scheme=2, want_lambda=False, **b)
+        assert repr(o["price"]) == c["price"]
+        a = np.ascontiguousarray(o["U"], dtype=np.float64) + 0.0
+        assert hashlib.sha256(a.tobytes()).hexdigest() == c["U_sha256"]
+
+
+def test_hundsdorfer_verwer_restatement_is_second_order_in_time(oracle):
+    """Scheme 3 (extension, parity unpinned): quartering dt cuts the time-stepping error more than tenfold (the kink of
+    the payoff keeps the first halving below the asymptotic factor four), where the Douglas scheme (theta = 0.8) is of
+    first order and only halves it per halving."""
+    kw = dict(m1=50, m2=25, theta=0.8, want_U=False, want_lambda=False, **BASE)
+    lim = oracle.solve(100.0, 2560, 1.0 / 2560, scheme=3, **kw)["price"]
+    e = [abs(oracle.solve(100.0, N, 1.0 / N, scheme=3, **kw)["price"] - lim) for N in (10, 20, 40)]
+    d = [abs(oracle.solve(100.0, N, 1.0 / N, scheme=0, **kw)["price"] - lim) for N in (10, 20, 40)]
+    assert e[0] / e[2] > 10.0 and e[0] > e[1] > e[2]
+    assert 1.8 < d[0] / d[1] < 2.2 and 1.8 < d[1] / d[2] < 2.2 and e[2] < d[2] / 10
