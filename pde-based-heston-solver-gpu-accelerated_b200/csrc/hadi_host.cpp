@@ -631,7 +631,10 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
                                         std::string(forced_variant ? forced_variant : "") + "|" +
                                             std::string(getenv("HADI_NO_DUO") ? getenv("HADI_NO_DUO") : ""));
   const auto plan_hit = ctx->plans.find(plan_key);
-  if (plan_hit != ctx->plans.end() && plan_hit->second.first == 0) {
+  const bool forced_wide = forced_variant && atoi(forced_variant) == HADI_WIDE_VARIANT;
+  if (forced_wide) {
+    plan.global_state = true;   // filled in below
+  } else if (plan_hit != ctx->plans.end() && plan_hit->second.first == 0) {
     plan = plan_hit->second.second;
   } else {
     const bool cs = num->scheme != HADI_DOUGLAS;   // the Craig-Sneyd family runs on the global-state kernels
@@ -651,6 +654,31 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
     if (prc < 0) return fail(ctx, HADI_ERR_SMEM, "grid too large: m1+1 <= 1024 and the coefficient tables must fit shared memory");
     if (prc > 0) return cuda_fail(ctx, (cudaError_t)prc, "kernel plan");
     ctx->plans[plan_key] = std::make_pair(0, plan);
+  }
+  // A few solves that need the global working set (large grids, the Craig-Sneyd family) and have no dividend jump: the
+  // wide kernel spreads each over a team of co-resident CTAs (hadi_wide.cu).  HADI_WIDE_MAX_ITEMS moves the threshold
+  // (0 disables); HADI_FORCE_VARIANT=9 takes it for any grid and batch size.
+  {
+    const char* wm = getenv("HADI_WIDE_MAX_ITEMS");
+    const int wide_max = wm ? atoi(wm) : HADI_WIDE_MAX_ITEMS_DEFAULT;
+    if (num->num_dividends == 0 && n_it_plan >= 1 &&
+        (forced_wide || (!forced_variant && plan.global_state && n_it_plan <= wide_max))) {
+      const auto wkey = std::make_tuple(num->m1, num->m2, num->scheme, 2, std::string("wide"));
+      auto wh = ctx->plans.find(wkey);
+      if (wh == ctx->plans.end()) {
+        HadiPlan wp;
+        const int wrc = hadi_wide_plan(ctx->device, m1, m2, g.ld, g.n1, g.n2, g.pj, &wp);
+        wh = ctx->plans.emplace(wkey, std::make_pair(wrc, wp)).first;
+      }
+      if (wh->second.first == 0) {
+        plan = wh->second.second;
+        plan.cluster = hadi_wide_team(n_it_plan, plan.sm_count, m1, m2);
+      } else if (forced_wide) {
+        return fail(ctx, HADI_ERR_SMEM, "the wide kernel does not take this grid");
+      }
+    } else if (forced_wide) {
+      return fail(ctx, HADI_ERR_ARG, "the wide kernel does not take dividend jumps");
+    }
   }
 
   std::unique_ptr<hadi_batch> b(new hadi_batch());
@@ -828,7 +856,7 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
   char* d_stage = (char*)take(staging, false);
   b->h_values = (double*)take(sizeof(double) * ((size_t)std::max(n_items, 1) * b->stride + 1), true);
   double* d_values = (double*)take(sizeof(double) * ((size_t)std::max(n_items, 1) * b->stride + 1), false);
-  int* d_counter = (int*)take(256, false);
+  int* d_counter = (int*)take(sizeof(int) * HADI_COUNTER_INTS, false);
 
   b->plan = plan;
   b->grid_ctas = std::max(1, std::min(n_items, plan.ctas_per_sm * plan.sm_count));
@@ -1005,7 +1033,7 @@ int hadi_batch_launch(hadi_batch* b) {
   if (!b) return HADI_ERR_ARG;
   hadi_ctx* ctx = b->ctx;
   cudaSetDevice(ctx->device);
-  cudaError_t e = cudaMemsetAsync(b->L.counter, 0, sizeof(int), ctx->stream);
+  cudaError_t e = cudaMemsetAsync(b->L.counter, 0, sizeof(int) * HADI_COUNTER_INTS, ctx->stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(b->L.reruns, 0, sizeof(unsigned long long), ctx->stream);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "memset");
   if (b->n_hand > 0) {
@@ -1014,7 +1042,8 @@ int hadi_batch_launch(hadi_batch* b) {
   }
   cudaEventRecord(b->ev0, ctx->stream);
   if (b->n_items > 0) {
-    const int rc = hadi_launch_douglas(b->L, b->plan, b->grid_ctas, ctx->stream);
+    const int rc = b->plan.variant == HADI_WIDE_VARIANT ? hadi_launch_wide(b->L, b->plan, b->grid_ctas, ctx->stream)
+                                                        : hadi_launch_douglas(b->L, b->plan, b->grid_ctas, ctx->stream);
     if (rc != 0) return cuda_fail(ctx, (cudaError_t)rc, "kernel launch");
     ctx->launches++;
   }

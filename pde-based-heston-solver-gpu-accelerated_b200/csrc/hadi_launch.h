@@ -123,3 +123,12 @@ HADI_HD HadiScratchLayout hadi_scratch_layout(int m1, int m2, int ld, int pj, bo
 int hadi_douglas_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj, bool need_global, HadiPlan* plan,
                       bool want_cluster = false);
 int hadi_launch_douglas(const HadiLaunch& L, const HadiPlan& plan, int grid_ctas, void* stream);
+
+// defined in hadi_wide.cu: one solve spread over a team of co-resident CTAs (co-operative launch); HadiPlan::cluster
+// carries the team size, set per batch with hadi_wide_team().  HadiLaunch::counter must hold HADI_COUNTER_INTS zeroed ints.
+#define HADI_WIDE_VARIANT 9
+#define HADI_WIDE_MAX_ITEMS_DEFAULT 18   /* batches up to this size of global-state solves go to the wide kernel */
+#define HADI_COUNTER_INTS 2048   /* work counter, cluster mailboxes, one barrier word per team (16 + 8 * team) */
+int hadi_wide_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj, HadiPlan* plan);
+int hadi_wide_team(int n_items, int sm_count, int m1, int m2);
+int hadi_launch_wide(const HadiLaunch& L, const HadiPlan& plan, int grid_ctas, void* stream);

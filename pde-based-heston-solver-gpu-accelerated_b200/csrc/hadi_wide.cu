@@ -1,0 +1,641 @@
+// hadi — the WIDE kernel: one solve spread over a TEAM of G co-resident CTAs (G up to one CTA per SM of the GPU).
+//
+// What bounds ONE large solve (401 x 201, 200 steps, Craig-Sneyd) is not memory or arithmetic throughput but the
+// dependent FP64 chain of its line solves: a forward / backward Thomas sweep along 400 nodes is 400 x (16 + 40)
+// cycles whoever runs it, and bit parity with the reference forbids re-associating it.  The lines of one sweep are
+// independent, so the fastest schedule gives every line its own thread ON ITS OWN WARP SCHEDULER, with every operand
+// of the chain already in shared memory, and lets all other work of the step disappear behind it:
+//
+//   * rows (A1 sweeps) are dealt round-robin to the CTAs of the team, columns (A2 sweeps) in contiguous blocks;
+//   * the point-wise stage that FEEDS a sweep is evaluated by the CTA that owns the line, straight into the
+//     shared-memory line buffer (predictor / corrector / explicit stage before an A1 sweep, the A2 right-hand side
+//     before an A2 sweep, the American projection after it) — no separate point-wise phase, no extra barrier;
+//   * the A1 factors of a CTA's rows stay in shared memory for the whole solve when they fit;
+//   * a step therefore has as many team barriers as it has row <-> column transpositions: 2 (Douglas) or 4
+//     (Craig-Sneyd family), each a release / acquire counter in global memory (the grid is launched co-operatively,
+//     every CTA is resident);
+//   * the state arrays (U with halo, Y, and Y0 / R0 / R1 / R2 for the Craig-Sneyd family) live in the L2-resident
+//     scratch block of the team and are read with ld.global.cg (other SMs write them between barriers).
+//
+// Arithmetic: the expressions of hadi_phases.cuh / hadi_phases_cs.cuh, operation for operation (the tables and the
+// factorisation ARE those functions); results are bit-identical to every other variant.  Guarded divisions use the
+// in-line IEEE fallback (hadi_div<false, true>), so there is no re-solve pass.
+//
+// Replaces, for batches of a few solves without dividend jumps, the thread-block-cluster kernel of round 1
+// (hadi_cluster_kernel, 8 CTAs, every phase through L2): 401 x 201 x 200 Craig-Sneyd 68 ms -> see DESIGN.md section 7.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdlib>
+
+#include "hadi_launch.h"
+#include "hadi_phases_cs.cuh"
+
+namespace {
+
+constexpr int kWideThreads = 512;
+constexpr int kWideWarps = kWideThreads / 32;
+constexpr int kCh = 4;   // nodes per register chunk of a chain
+
+__device__ __forceinline__ double wld(const double* p) { return __ldcg(p); }
+
+// ---- team barrier ------------------------------------------------------------------------------------------------
+struct WideTeam {
+  unsigned* ctr;    // monotonic arrival counter of the team (zeroed by the host before the launch)
+  unsigned epoch;   // arrivals after which the next barrier opens (thread 0 only)
+  int G;
+};
+__device__ __forceinline__ void wide_sync(WideTeam& tm, int tid) {
+  __syncthreads();
+  if (tm.G > 1 && tid == 0) {
+    tm.epoch += (unsigned)tm.G;
+    __threadfence();
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(tm.ctr) : "memory");
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(tm.ctr) : "memory");
+    } while ((int)(v - tm.epoch) < 0);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// ---- ownership and shared-memory line buffers -----------------------------------------------------------------------
+struct WideGeo {
+  int rank, G;
+  int nrow;          // owned rows: rank + G*k, k < nrow
+  int c0, ncol;      // owned columns [c0, c0 + ncol)
+  int RB, CB;        // lines per batch
+  int pr, pc;        // pitches (doubles) of a row / column buffer
+  bool resident;     // every owned row fits one batch: its A1 factors are loaded once per solve
+  double *ry, *rd, *rm, *rt, *ru;   // [RB][pr] right-hand side -> solution | forward result | multipliers |
+                                    // [RB][2*pr] pivot, prepared reciprocal (back-substitution order) | impl_upper
+  double *cb, *cd, *cl;             // [CB][pc] right-hand side -> solution | forward result | lambda
+};
+
+// the 11 neighbours of node (j, i) the explicit operators need
+struct WideNb {
+  double mm, m0, mp, zm, z0, zp, pm, p0, pp, m2, p2;
+};
+__device__ __forceinline__ WideNb wide_nb(const double* X, int ld, int i, int j) {
+  const double* p = X + j * ld + i;
+  WideNb n;
+  n.mm = wld(p - ld - 1); n.m0 = wld(p - ld); n.mp = wld(p - ld + 1);
+  n.zm = wld(p - 1); n.z0 = wld(p); n.zp = wld(p + 1);
+  n.pm = wld(p + ld - 1); n.p0 = wld(p + ld); n.pp = wld(p + ld + 1);
+  n.m2 = wld(p - 2 * ld); n.p2 = wld(p + 2 * ld);
+  return n;
+}
+// A0 product, l outer, k inner (hadi_cs_a0 / phase E)
+__device__ __forceinline__ double wide_a0(const HadiView& w, const WideNb& n, int i, int j) {
+  const double rs = hadi_ti(w, TI_RS)[i];
+  const double bsm = hadi_ti(w, TI_BSM)[i], bs0 = hadi_ti(w, TI_BS0)[i], bsp = hadi_ti(w, TI_BSP)[i];
+  const double* tj = w.tj;
+  const int n2 = w.n2;
+  const double cij = rs * tj[TJ_V * n2 + j];
+  const double csm = cij * bsm, cs0 = cij * bs0, csp = cij * bsp;
+  const double bm = tj[TJ_BVM * n2 + j], b0 = tj[TJ_BV0 * n2 + j], bp = tj[TJ_BVP * n2 + j];
+  double r0 = (csm * bm) * n.mm;
+  r0 += (cs0 * bm) * n.m0;
+  r0 += (csp * bm) * n.mp;
+  r0 += (csm * b0) * n.zm;
+  r0 += (cs0 * b0) * n.z0;
+  r0 += (csp * b0) * n.zp;
+  r0 += (csm * bp) * n.pm;
+  r0 += (cs0 * bp) * n.p0;
+  r0 += (csp * bp) * n.pp;
+  return r0;
+}
+// A1 coefficients of node (j, i)
+__device__ __forceinline__ void wide_a1c(const HadiView& w, int i, int j, double& lo, double& ma, double& up) {
+  const double a = hadi_ti(w, TI_HS2)[i] * w.tj[TJ_V * w.n2 + j];
+  lo = a * hadi_ti(w, TI_DSM)[i] + hadi_ti(w, TI_BBM)[i];
+  ma = a * hadi_ti(w, TI_DS0)[i] + hadi_ti(w, TI_BB0)[i] - hadi_ti(w, TI_HRD)[i];
+  up = a * hadi_ti(w, TI_DSP)[i] + hadi_ti(w, TI_BBP)[i];
+}
+// A1 product in the host order of the Craig-Sneyd family: main, lower, upper (hadi_cs_predict)
+__device__ __forceinline__ double wide_a1_host(const HadiView& w, const WideNb& n, int i, int j) {
+  double lo, ma, up;
+  wide_a1c(w, i, j, lo, ma, up);
+  double r1 = ma * n.z0;
+  if (i > 0) r1 += lo * n.zm;
+  if (i < w.m1) r1 += up * n.zp;
+  return r1;
+}
+__device__ __forceinline__ double wide_a2(const HadiView& w, const WideNb& n, int j) {
+  const double* tj = w.tj;
+  const int n2 = w.n2;
+  double r2 = tj[TJ_L2 * n2 + j] * n.m2 + tj[TJ_L1 * n2 + j] * n.m0 + tj[TJ_D0 * n2 + j] * n.z0 + tj[TJ_U1 * n2 + j] * n.p0;
+  r2 += tj[TJ_U2 * n2 + j] * n.p2;
+  return r2;
+}
+
+// ---- right-hand sides of the A1 sweeps, one node ----------------------------------------------------------------------
+// Douglas explicit stage (hadi_phase_explicit)
+__device__ __forceinline__ double wide_node_explicit(const HadiItem& it, const HadiView& w, double e0, double e1, int i,
+                                                     int j) {
+  const int m1 = w.m1, m2 = w.m2;
+  const double dt = it.dt, c = w.c;
+  const bool am = it.style == 1;
+  const WideNb n = wide_nb(w.U, w.ld, i, j);
+  const double x = n.z0;
+  const double r0 = wide_a0(w, n, i, j);
+  double lo, ma, upc;
+  wide_a1c(w, i, j, lo, ma, upc);
+  const double r1 = lo * n.zm + ma * x + upc * n.zp;
+  const double r2 = wide_a2(w, n, j);
+  const double lam_cur = am ? wld(w.lam + j * w.ld + i) : 0.0;
+  const bool is_b1 = (i + j == m1);
+  double y;
+  if (is_b1 || j == m2) {
+    const double b1v = it.bc ? 0.0 : (it.r_d - it.r_f) * hadi_ti(w, TI_S)[m1] * it.ef;
+    const double b1p = is_b1 ? b1v : 0.0;
+    const double b2p = (j == m2) ? hadi_ti(w, TI_B2V)[i] : 0.0;
+    const double bp_ = 0.0 + b1p + b2p;
+    double sum = r0 + r1 + r2 + bp_ * e0;
+    if (am) sum = sum + lam_cur;
+    y = x + dt * sum;
+    y = y + c * (b1p * e1 - (r1 + b1p * e0));
+  } else {
+    double sum = r0 + r1 + r2;
+    if (am) sum = sum + lam_cur;
+    y = x + dt * sum;
+    y = y - c * r1;
+  }
+  return y;
+}
+// Craig-Sneyd family, predictor (hadi_cs_predict): keeps R0, R1, R2, Y0 of the node
+__device__ __forceinline__ double wide_node_predict(const HadiItem& it, const HadiView& w, const HadiCsView& cs, double e0,
+                                                    double e1, int i, int j, int scheme) {
+  const double dt = it.dt, c = w.c;
+  const WideNb n = wide_nb(w.U, w.ld, i, j);
+  const double x = n.z0;
+  const double r0 = wide_a0(w, n, i, j);
+  const double r1 = wide_a1_host(w, n, i, j);
+  const double r2 = wide_a2(w, n, j);
+  double b1p, b2p;
+  hadi_cs_bounds(it, w, i, j, b1p, b2p);
+  const double bb = 0.0 + b1p + b2p;
+  const double y0 = x + dt * (r0 + r1 + r2 + bb * e0);
+  const int q = j * w.ld + i;
+  cs.R0[q] = r0;
+  cs.R1[q] = r1;
+  cs.R2[q] = r2;
+  const double rhs = y0 + c * (b1p * e1 - (r1 + b1p * e0));
+  cs.Y0[q] = (scheme == HADI_SCHEME_MCS) ? rhs : y0;
+  return rhs;
+}
+// correctors (hadi_cs_correct, hadi_cs_correct2); Y2 sits in U
+__device__ __forceinline__ double wide_node_correct(const HadiItem& it, const HadiView& w, const HadiCsView& cs, double e0,
+                                                    double e1, int i, int j, int scheme) {
+  const double dt = it.dt, c = w.c, theta = it.theta;
+  const WideNb n = wide_nb(w.U, w.ld, i, j);
+  const double a0y2 = wide_a0(w, n, i, j);
+  double b1p, b2p;
+  hadi_cs_bounds(it, w, i, j, b1p, b2p);
+  const int q = j * w.ld + i;
+  if (scheme == HADI_SCHEME_CS) {
+    const double y0t = wld(cs.Y0 + q) + 0.5 * dt * ((a0y2 + 0.0 * e1) - (wld(cs.R0 + q) + 0.0 * e0));
+    return y0t + c * (b1p * e1 - (wld(cs.R1 + q) + b1p * e0));
+  }
+  const double a1y2 = wide_a1_host(w, n, i, j);
+  const double a2y2 = wide_a2(w, n, j);
+  const double bb = 0.0 + b1p + b2p;
+  const double R0 = wld(cs.R0 + q), R1 = wld(cs.R1 + q), R2 = wld(cs.R2 + q);
+  const double prev = R0 + R1 + R2 + bb * e0;
+  const double curr = a0y2 + a1y2 + a2y2 + bb * e1;
+  if (scheme == HADI_SCHEME_MCS) {
+    const double f0n = a0y2 + 0.0 * e1, f0m = R0 + 0.0 * e0;
+    const double y0h = wld(cs.Y0 + q) + c * (f0n - f0m);
+    const double y0t = y0h + (0.5 - theta) * dt * (curr - prev);
+    return y0t + c * (b1p * e1 - (R1 + b1p * e0));
+  }
+  const double y0t = wld(cs.Y0 + q) + 0.5 * dt * (curr - prev);
+  cs.R2[q] = a2y2;   // Hundsdorfer-Verwer: the second A2 right-hand side is centred on Y2
+  return y0t + c * (b1p * e1 - (a1y2 + b1p * e1));
+}
+
+// ---- the chains: one thread per line, every operand in shared memory, next chunk's operands in flight --------------------
+// A1 (hadi_phase_solve_a1): forward x_i = y_i - m_i x_{i-1}; back x_i = (x_i - impl_upper_i x_{i+1}) / pivot_i
+__device__ __forceinline__ void wide_chain_a1(double* __restrict__ y, double* __restrict__ d, const double* __restrict__ m,
+                                              const double* __restrict__ tb, const double* __restrict__ iu, int m1) {
+  unsigned bad = 0;
+  double x = y[0];
+  d[0] = x;
+  {
+    double yy[kCh], mm[kCh];
+#pragma unroll
+    for (int k = 0; k < kCh; ++k) { yy[k] = y[1 + k]; mm[k] = m[k]; }
+    for (int ib = 1; ib <= m1; ib += kCh) {
+      double ny[kCh], nm[kCh];
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) { ny[k] = y[ib + kCh + k]; nm[k] = m[ib + kCh - 1 + k]; }   // buffers are padded by 2 chunks
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) {
+        if (ib + k <= m1) {
+          x = yy[k] - mm[k] * x;
+          d[ib + k] = x;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) { yy[k] = ny[k]; mm[k] = nm[k]; }
+    }
+  }
+  double xn = 0.0;
+  {
+    // element k of the back-substitution order is node i = m1 - k
+    double tt[kCh], rr[kCh], dd[kCh], uu[kCh];
+#pragma unroll
+    for (int k = 0; k < kCh; ++k) {
+      const int i = (m1 - k >= 1) ? m1 - k : 1;
+      tt[k] = tb[2 * k]; rr[k] = tb[2 * k + 1]; dd[k] = d[i]; uu[k] = iu[i];
+    }
+    for (int kb = 0; kb < m1; kb += kCh) {
+      double nt[kCh], nr[kCh], nd[kCh], nu[kCh];
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) {
+        const int kk = kb + kCh + k;
+        const int i = (m1 - kk >= 1) ? m1 - kk : 1;
+        nt[k] = tb[2 * kk]; nr[k] = tb[2 * kk + 1]; nd[k] = d[i]; nu[k] = iu[i];
+      }
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) {
+        const int i = m1 - kb - k;
+        if (i >= 1) {
+          x = hadi_div<false, true>(dd[k] - uu[k] * xn, tt[k], rr[k], bad);
+          xn = x;
+          y[i] = x;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) { tt[k] = nt[k]; rr[k] = nr[k]; dd[k] = nd[k]; uu[k] = nu[k]; }
+    }
+  }
+  y[0] = d[0];
+}
+// A2 (hadi_phase_solve_a2): d_j = (b_j - f_j d_{j-1} - g_j d_{j-2}) m_j; x_j = d_j - c'_j x_{j+1} - c2'_j x_{j+2}
+__device__ __forceinline__ void wide_chain_a2(double* __restrict__ b, double* __restrict__ d, const double* __restrict__ F,
+                                              const double* __restrict__ G, const double* __restrict__ MM,
+                                              const double* __restrict__ CP, const double* __restrict__ C2P, int m2) {
+  unsigned bad = 0;
+  double d1 = hadi_div<false, true>(b[0], MM[0], G[0], bad);
+  double d2 = 0.0;
+  d[0] = d1;
+  {
+    double bb[kCh], ff[kCh], gg[kCh], mm[kCh];
+#pragma unroll
+    for (int k = 0; k < kCh; ++k) {
+      const int j = (1 + k <= m2) ? 1 + k : m2;
+      bb[k] = b[j]; ff[k] = F[j]; gg[k] = G[j]; mm[k] = MM[j];
+    }
+    for (int jb = 1; jb <= m2; jb += kCh) {
+      double nb[kCh], nf[kCh], ng[kCh], nm[kCh];
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) {
+        const int j = (jb + kCh + k <= m2) ? jb + kCh + k : m2;
+        nb[k] = b[j]; nf[k] = F[j]; ng[k] = G[j]; nm[k] = MM[j];
+      }
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) {
+        if (jb + k <= m2) {
+          const double v = (bb[k] - ff[k] * d1 - gg[k] * d2) * mm[k];
+          d[jb + k] = v;
+          d2 = d1;
+          d1 = v;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) { bb[k] = nb[k]; ff[k] = nf[k]; gg[k] = ng[k]; mm[k] = nm[k]; }
+    }
+  }
+  double x1 = 0.0, x2 = 0.0;
+  {
+    double dd[kCh], cc[kCh], c2[kCh];
+#pragma unroll
+    for (int k = 0; k < kCh; ++k) {
+      const int j = (m2 - k >= 0) ? m2 - k : 0;
+      dd[k] = d[j]; cc[k] = CP[j]; c2[k] = C2P[j];
+    }
+    for (int jt = m2; jt >= 0; jt -= kCh) {
+      double nd[kCh], nc[kCh], n2[kCh];
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) {
+        const int j = (jt - kCh - k >= 0) ? jt - kCh - k : 0;
+        nd[k] = d[j]; nc[k] = CP[j]; n2[k] = C2P[j];
+      }
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) {
+        if (jt - k >= 0) {
+          const double x = dd[k] - cc[k] * x1 - c2[k] * x2;
+          x2 = x1;
+          x1 = x;
+          b[jt - k] = x;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) { dd[k] = nd[k]; cc[k] = nc[k]; c2[k] = n2[k]; }
+    }
+  }
+}
+// line r of a batch runs on lane r / warps of warp r % warps: the first 16 lines sit on 16 different warps
+__device__ __forceinline__ int wide_line_of_thread(int tid) { return (tid & 31) * kWideWarps + (tid >> 5); }
+
+// ---- stages -------------------------------------------------------------------------------------------------------------
+// A1 factor streams of owned row (batch slot r, row j) into the row buffers
+__device__ __forceinline__ void wide_load_factors(const HadiItem& it, const HadiView& w, const WideGeo& g, int r, int j,
+                                                  int tid) {
+  const int m1 = w.m1;
+  const double* fM = w.fM + (size_t)j * w.co_pi;
+  const double* fB = w.fB + (size_t)j * w.co_pi * 2;
+  const double vj = w.tj[TJ_V * w.n2 + j];
+  const double theta = it.theta, dt = it.dt;
+  for (int k = tid; k < m1; k += kWideThreads) {
+    g.rm[r * g.pr + k] = wld(fM + k);
+    g.rt[r * 2 * g.pr + 2 * k] = wld(fB + 2 * k);
+    g.rt[r * 2 * g.pr + 2 * k + 1] = wld(fB + 2 * k + 1);
+  }
+  for (int i = tid; i <= m1; i += kWideThreads) {
+    const double a = hadi_ti(w, TI_HS2)[i] * vj;
+    const double up = a * hadi_ti(w, TI_DSP)[i] + hadi_ti(w, TI_BBP)[i];
+    g.ru[r * g.pr + i] = -theta * dt * up;
+  }
+}
+
+// kind: 0 Douglas explicit stage, 1 Craig-Sneyd-family predictor, 2 corrector
+template <int KIND>
+__device__ __forceinline__ void wide_rows(const HadiItem& it, const HadiView& w, const HadiCsView& cs, const WideGeo& g,
+                                          double e0, double e1, int scheme, int tid) {
+  const int m1 = w.m1, nc = m1 + 1;
+  for (int b0 = 0; b0 < g.nrow; b0 += g.RB) {
+    const int nb = min(g.RB, g.nrow - b0);
+    if (!g.resident)
+      for (int r = 0; r < nb; ++r) wide_load_factors(it, w, g, r, g.rank + g.G * (b0 + r), tid);
+    for (int idx = tid; idx < nb * nc; idx += kWideThreads) {
+      const int r = idx / nc, i = idx - r * nc;
+      const int j = g.rank + g.G * (b0 + r);
+      double rhs;
+      if (KIND == 0) rhs = wide_node_explicit(it, w, e0, e1, i, j);
+      else if (KIND == 1) rhs = wide_node_predict(it, w, cs, e0, e1, i, j, scheme);
+      else rhs = wide_node_correct(it, w, cs, e0, e1, i, j, scheme);
+      g.ry[r * g.pr + i] = rhs;
+    }
+    __syncthreads();
+    {
+      const int r = wide_line_of_thread(tid);
+      if (r < nb)
+        wide_chain_a1(g.ry + r * g.pr, g.rd + r * g.pr, g.rm + r * g.pr, g.rt + r * 2 * g.pr, g.ru + r * g.pr, m1);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nb * nc; idx += kWideThreads) {
+      const int r = idx / nc, i = idx - r * nc;
+      const int j = g.rank + g.G * (b0 + r);
+      w.Y[j * w.ld + i] = g.ry[r * g.pr + i];
+    }
+    if (b0 + g.RB < g.nrow) __syncthreads();
+  }
+}
+
+// A2 sweeps of the owned columns.  douglas: the right-hand side re-derives A2 U from the old solution (hadi_phase_rhs2),
+// the Dirichlet column of the put boundary set and the American projection follow the sweep (hadi_phase_project);
+// otherwise the right-hand side takes the stored R2 (hadi_cs_rhs2).
+__device__ __forceinline__ void wide_cols(const HadiItem& it, const HadiView& w, const HadiCsView& cs, const WideGeo& g,
+                                          double e0, double e1, bool douglas, double g_dir, double rdt, int tid) {
+  const int m2 = w.m2, ld = w.ld, n2 = w.n2, nr = m2 + 1;
+  const double c = w.c, dt = it.dt;
+  const bool am = douglas && it.style == 1;
+  const double* tj = w.tj;
+  for (int b0 = 0; b0 < g.ncol; b0 += g.CB) {
+    const int nb = min(g.CB, g.ncol - b0);
+    for (int idx = tid; idx < nb * nr; idx += kWideThreads) {
+      const int j = idx / nb, cc = idx - j * nb;
+      const int i = g.c0 + b0 + cc;
+      const int q = j * ld + i;
+      const double y = wld(w.Y + q);
+      double v;
+      if (douglas) {
+        const double* p = w.U + q;
+        double r2 = tj[TJ_L2 * n2 + j] * wld(p - 2 * ld) + tj[TJ_L1 * n2 + j] * wld(p - ld) + tj[TJ_D0 * n2 + j] * wld(p) +
+                    tj[TJ_U1 * n2 + j] * wld(p + ld);
+        r2 += tj[TJ_U2 * n2 + j] * wld(p + 2 * ld);
+        const double b2 = (j == m2) ? hadi_ti(w, TI_B2V)[i] : 0.0;
+        v = y + c * (b2 * e1 - (r2 + b2 * e0));
+        if (am) g.cl[cc * g.pc + j] = wld(w.lam + q);
+      } else {
+        double b1p, b2p;
+        hadi_cs_bounds(it, w, i, j, b1p, b2p);
+        v = y + c * (b2p * e1 - (wld(cs.R2 + q) + b2p * e0));
+      }
+      g.cb[cc * g.pc + j] = v;
+    }
+    __syncthreads();
+    {
+      const int cc = wide_line_of_thread(tid);
+      if (cc < nb)
+        wide_chain_a2(g.cb + cc * g.pc, g.cd + cc * g.pc, tj + TJ_F * n2, tj + TJ_G * n2, tj + TJ_MM * n2, tj + TJ_CP * n2,
+                      tj + TJ_C2P * n2, m2);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nb * nr; idx += kWideThreads) {
+      const int j = idx / nb, cc = idx - j * nb;
+      const int i = g.c0 + b0 + cc;
+      const int q = j * ld + i;
+      double x = g.cb[cc * g.pc + j];
+      if (douglas && it.bc && i == 0) x = g_dir;
+      if (am) {
+        unsigned bad = 0;
+        const double u0 = hadi_ti(w, TI_PAY)[i];
+        const double l = g.cl[cc * g.pc + j];
+        const double ln = hadi_max(0.0, l + hadi_div<false, true>(u0 - x, dt, rdt, bad));
+        w.lam[q] = (i == w.m1) ? 0.0 : ln;
+        x = hadi_max(x - dt * l, u0);
+      }
+      w.U[q] = x;
+    }
+    if (b0 + g.CB < g.ncol) __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kWideThreads, 1) hadi_wide_kernel(const HadiLaunch L, const int G) {
+  extern __shared__ double smem[];
+  const int tid = threadIdx.x;
+  const int team = blockIdx.x / G, rank = blockIdx.x - team * G, n_teams = gridDim.x / G;
+  const int m1 = L.m1, m2 = L.m2;
+  HadiView w;
+  w.m1 = m1; w.m2 = m2; w.P = (m1 + 1) * (m2 + 1);
+  w.ld = L.ld; w.n1 = L.n1; w.n2 = L.n2; w.pj = L.pj;
+  w.line_mul = G; w.line_off = rank;
+  w.co_pi = (m1 + 7) & ~7;
+  // shared memory: per-i tables | per-j tables | dividend index (unused) | arena (A2 assembly scratch during set-up, then line buffers)
+  double* sp = smem;
+  w.ti = sp; sp += (size_t)TI_COUNT * w.n1;
+  w.tj = sp; sp += (size_t)TJ_COUNT * w.n2;
+  w.divk = nullptr;
+  double* arena = sp;
+  const int arena_doubles = L.dbg_phase;   // set by hadi_launch_wide: doubles of shared memory behind the tables
+  double* scratch = L.scratch + (size_t)team * L.scratch_stride;
+  const HadiScratchLayout gl = hadi_scratch_layout(m1, m2, w.ld, w.pj, true, L.scheme >= 1);
+  double* Ualloc = scratch + gl.U;
+  w.U = Ualloc + HADI_HALO * w.ld + 1;
+  w.Y = scratch + gl.Y;
+  w.fM = scratch + gl.fM;
+  w.fB = scratch + gl.fB;
+  w.lam = scratch + gl.lam;
+  HadiCsView cs;
+  cs.Y0 = scratch + gl.Y0; cs.R0 = scratch + gl.R0; cs.R1 = scratch + gl.R1; cs.R2 = scratch + gl.R2;
+
+  WideGeo g;
+  g.rank = rank; g.G = G;
+  g.nrow = (rank <= m2) ? (m2 - rank) / G + 1 : 0;
+  g.c0 = (int)(((long long)rank * (m1 + 1)) / G);
+  g.ncol = (int)(((long long)(rank + 1) * (m1 + 1)) / G) - g.c0;
+  g.pr = w.n1 + 2 * kCh;
+  g.pc = (w.n2 + 2 * kCh) | 1;
+  const int max_row = (m2 + G) / G, max_col = (m1 + G) / G;
+  g.RB = min(max_row, arena_doubles / (6 * g.pr));
+  g.CB = min(max_col, arena_doubles / (3 * g.pc));
+  g.resident = max_row <= g.RB;
+  g.ry = arena;
+  g.rd = g.ry + (size_t)g.RB * g.pr;
+  g.rm = g.rd + (size_t)g.RB * g.pr;
+  g.ru = g.rm + (size_t)g.RB * g.pr;
+  g.rt = g.ru + (size_t)g.RB * g.pr;
+  g.cb = arena;
+  g.cd = g.cb + (size_t)g.CB * g.pc;
+  g.cl = g.cd + (size_t)g.CB * g.pc;
+  // the row buffers of a resident team member hold its factors for the whole solve: the column buffers then sit behind them
+  if (g.resident) {
+    const int used = 6 * g.RB * g.pr;
+    g.CB = min(max_col, (arena_doubles - used) / (3 * g.pc));
+    g.cb = arena + used;
+    g.cd = g.cb + (size_t)g.CB * g.pc;
+    g.cl = g.cd + (size_t)g.CB * g.pc;
+  }
+
+  WideTeam tm;
+  tm.ctr = reinterpret_cast<unsigned*>(L.counter) + 16 + 8 * team;
+  tm.epoch = 0;
+  tm.G = G;
+  const int gtid = rank * kWideThreads + tid, gnt = G * kWideThreads;
+  for (int k = gtid; k < (m2 + 1 + 2 * HADI_HALO) * w.ld + 2; k += gnt) Ualloc[k] = 0.0;
+
+  for (int item = team; item < L.n_items; item += n_teams) {
+    const HadiItem it = L.items[item];
+    const double* sg = L.s_pool + it.s_off;
+    const double* vg = L.v_pool + it.v_off;
+    const double* eg = L.e_pool + it.e_off;
+    w.c = it.theta * it.dt;
+    const double rdt = hadi_rcp_prep(it.dt);
+    {
+      // tables and factorisation: hadi_phases.cuh, with the A2 assembly scratch in the (still unused) arena.  The view
+      // is re-aimed in place: a by-value copy of it came out of nvcc 12.9 with line_mul / line_off / co_pi undefined.
+      double* const y_keep = w.Y;
+      w.Y = arena;
+      w.ts_off = 0;
+      hadi_phase_tables(it, w, sg, vg, tid, kWideThreads);
+      __syncthreads();
+      hadi_phase_factor(it, w, vg, tid, kWideThreads, kWideThreads - 1);
+      __syncthreads();
+      w.Y = y_keep;
+    }
+    for (int p = gtid; p < (m2 + 1) * (m1 + 1); p += gnt) {
+      const int j = p / (m1 + 1), i = p - j * (m1 + 1);
+      w.U[j * w.ld + i] = hadi_ti(w, TI_PAY)[i];
+      if (it.style == 1) w.lam[j * w.ld + i] = 0.0;
+    }
+    if (g.resident)
+      for (int r = 0; r < g.nrow; ++r) wide_load_factors(it, w, g, r, rank + G * r, tid);
+    wide_sync(tm, tid);
+    for (int n = 1; n <= it.N; ++n) {
+      const double e0 = eg[n - 1], e1 = eg[n];
+      if (L.scheme >= 1) {
+        wide_rows<1>(it, w, cs, g, e0, e1, L.scheme, tid);
+        wide_sync(tm, tid);
+        wide_cols(it, w, cs, g, e0, e1, false, 0.0, rdt, tid);   // Y2 -> U
+        wide_sync(tm, tid);
+        wide_rows<2>(it, w, cs, g, e0, e1, L.scheme, tid);
+        wide_sync(tm, tid);
+        wide_cols(it, w, cs, g, L.scheme == HADI_SCHEME_HV ? e1 : e0, e1, false, 0.0, rdt, tid);
+        wide_sync(tm, tid);
+      } else {
+        wide_rows<0>(it, w, cs, g, e0, e1, 0, tid);
+        wide_sync(tm, tid);
+        wide_cols(it, w, cs, g, e0, e1, true, it.bc ? it.K * eg[it.N + 1 + n] : 0.0, rdt, tid);
+        wide_sync(tm, tid);
+      }
+    }
+    if (gtid == 0) {
+      if (L.out_stride <= 1) {
+        L.out_values[it.out] = wld(w.U + it.idx_v * w.ld + it.idx_s);
+      } else {
+        double* o = L.out_values + (size_t)it.out * L.out_stride;
+        o[0] = wld(w.U + it.idx_v * w.ld + it.idx_s);
+        o[1] = wld(w.U + (it.aux & 0xffff) * w.ld + it.idx_s);
+        o[2] = wld(w.U + ((it.aux >> 16) & 0xffff) * w.ld + it.idx_s);
+      }
+    }
+    if (L.out_U != nullptr || L.out_lam != nullptr) {
+      for (int p = gtid; p < (m2 + 1) * (m1 + 1); p += gnt) {
+        const int j = p / (m1 + 1), i = p - j * (m1 + 1);
+        const size_t o = (size_t)it.out * w.P + (size_t)p;
+        if (L.out_U != nullptr) L.out_U[o] = wld(w.U + j * w.ld + i);
+        if (L.out_lam != nullptr && it.style == 1) L.out_lam[o] = wld(w.lam + j * w.ld + i);
+      }
+    }
+    wide_sync(tm, tid);   // everyone is done with U and the tables before the next item
+  }
+}
+
+size_t wide_table_bytes(int n1, int n2) { return sizeof(double) * ((size_t)TI_COUNT * n1 + (size_t)TJ_COUNT * n2); }
+
+}  // namespace
+
+// Shared memory: the tables plus an arena that must take the A2 assembly scratch, one row batch and one column batch.
+int hadi_wide_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj, HadiPlan* plan) {
+  (void)ld; (void)pj;
+  int max_smem = 0, sms = 0;
+  cudaError_t e = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  if (e != cudaSuccess) return (int)e;
+  if (m2 + 1 > kWideThreads - 1 || m1 + 1 > 4096) return -1;
+  const size_t tables = wide_table_bytes(n1, n2);
+  const size_t pr = (size_t)n1 + 2 * kCh, pc = ((size_t)n2 + 2 * kCh) | 1;
+  const size_t need = tables + sizeof(double) * std::max((size_t)TS_COUNT * n2, 6 * pr + 3 * pc);
+  if (need + 1024 > (size_t)max_smem) return -1;
+  const size_t smem = ((size_t)max_smem - 1024) & ~size_t(127);   // take the SM: one CTA per SM, the arena as large as it gets
+  e = cudaFuncSetAttribute((const void*)hadi_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)hadi_wide_kernel, kWideThreads, smem);
+  if (e != cudaSuccess) return (int)e;
+  if (occ < 1) return -1;
+  plan->global_state = true;
+  plan->variant = HADI_WIDE_VARIANT;
+  plan->threads = kWideThreads;
+  plan->ctas_per_sm = 1;
+  plan->sm_count = sms;
+  plan->smem_bytes = smem;
+  plan->cluster = 1;   // team size: set per batch by the host layer (hadi_wide_team)
+  plan->duo = 1;
+  return 0;
+}
+
+// CTAs per solve for a batch of n_items on sm_count SMs: everything the GPU has, but no more CTAs than lines
+int hadi_wide_team(int n_items, int sm_count, int m1, int m2) {
+  const int lines = std::max(m1 + 1, m2 + 1);
+  return std::max(1, std::min(sm_count / std::max(1, n_items), lines));
+}
+
+int hadi_launch_wide(const HadiLaunch& L_in, const HadiPlan& plan, int grid_ctas, void* stream) {
+  HadiLaunch L = L_in;
+  int G = plan.cluster;
+  if (G < 1 || grid_ctas % G != 0) return (int)cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute((const void*)hadi_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes);
+  if (e != cudaSuccess) return (int)e;
+  L.dbg_phase = (int)((plan.smem_bytes - wide_table_bytes(L.n1, L.n2)) / sizeof(double));   // arena size, doubles
+  L.dbg_step = 0;
+  void* args[] = {(void*)&L, (void*)&G};
+  // co-operative launch: the runtime refuses a grid whose CTAs cannot all be resident (the team barrier needs them)
+  e = cudaLaunchCooperativeKernel((const void*)hadi_wide_kernel, dim3((unsigned)grid_ctas), dim3(kWideThreads), args, plan.smem_bytes,
+                                  (cudaStream_t)stream);
+  return (int)e;
+}

@@ -369,6 +369,50 @@ def test_large_grid_one_cta_and_cluster_kernels(hadi, ctx, oracle, monkeypatch, 
     assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("m1,m2", [(300, 150), (100, 50), (37, 19)])
+def test_wide_kernel_is_bit_equal(hadi, ctx, oracle, monkeypatch, m1, m2):
+    """The wide kernel (hadi_wide.cu, variant 9: one solve on a team of co-resident CTAs, rows and columns of the line
+    solves dealt to the team, team barriers through L2): every scheme and option style it takes, on one solve (team of
+    148 CTAs), on a few (teams of 29) and on more items than teams, against the oracle and against the one-CTA kernels."""
+    monkeypatch.setenv("HADI_FORCE_VARIANT", "9")
+    N = 4
+    mdl = hadi.make_model(**BASE)
+    o = oracle.solve(100.0, N, 1.0 / 100, m1=m1, m2=m2, theta=0.8, want_lambda=False, **BASE)
+    g = solve_gpu(hadi, ctx, [100.0], N, N / 100.0, m1, m2)
+    assert g["prices"][0] == o["price"] and np.array_equal(g["U"][0], o["U"])
+    o = oracle.solve(100.0, N, 1.0 / 100, m1=m1, m2=m2, theta=0.8, style=1, **BASE)
+    g = solve_gpu(hadi, ctx, [100.0, 100.0, 100.0, 100.0, 100.0], N, N / 100.0, m1, m2, style=1)
+    for k in (0, 4):
+        assert g["prices"][k] == o["price"] and np.array_equal(g["U"][k], o["U"])
+        assert np.array_equal(g["lambda"][k], o["lambda"])
+    for scheme in (1, 2, 3):
+        o = oracle.solve(104.0, N, 1.0 / 100, m1=m1, m2=m2, theta=0.8, scheme=scheme, want_lambda=False, **BASE)
+        num = hadi.make_numerics(m1, m2, 0.8, hadi.EUROPEAN, hadi.CALL, scheme, None)
+        pts, n = hadi.make_points([104.0, 93.0], N / 100.0, N)
+        g = ctx.price_batch(mdl, num, pts, n, want_U=True)
+        assert g["prices"][0] == o["price"] and np.array_equal(g["U"][0], o["U"])
+    # put-correct boundary set (Dirichlet column), American
+    o = oracle.solve(93.0, N, 1.0 / N, m1=m1, m2=m2, theta=0.8, style=1, payoff_put=1, bc=1, **BASE)
+    num = hadi.make_numerics(m1, m2, 0.8, 1, hadi.PUT, hadi.DOUGLAS, None, boundary=hadi.BC_PUT)
+    pts, n = hadi.make_points([93.0], 1.0, N)
+    g = ctx.price_batch(mdl, num, pts, n, want_U=True, want_lambda=True)
+    assert g["prices"][0] == o["price"] and np.array_equal(g["U"][0], o["U"]) and np.array_equal(g["lambda"][0], o["lambda"])
+    # more items than teams, mixed step counts; against the default kernels
+    strikes = [90.0 + 0.1 * k for k in range(200)]
+    a = solve_gpu(hadi, ctx, strikes, N, N / 100.0, m1, m2)["prices"]
+    monkeypatch.delenv("HADI_FORCE_VARIANT")
+    monkeypatch.setenv("HADI_WIDE_MAX_ITEMS", "0")
+    b = solve_gpu(hadi, ctx, strikes, N, N / 100.0, m1, m2)["prices"]
+    assert np.array_equal(a, b)
+    # interpolated-V0 Jacobian publishes three values per item
+    num = hadi.make_numerics(m1, m2, 0.8)
+    pts, n = hadi.make_points([92.0, 100.0], 1.0, N)
+    Jb, baseb = ctx.jacobian_batch_ex(mdl, num, pts, n, hadi.MODE_JACOBIAN_INTERP, 1e-6)
+    monkeypatch.setenv("HADI_FORCE_VARIANT", "9")
+    Ja, basea = ctx.jacobian_batch_ex(mdl, num, pts, n, hadi.MODE_JACOBIAN_INTERP, 1e-6)
+    assert np.array_equal(Ja, Jb) and np.array_equal(basea, baseb)
+
+
 def test_config4_full_size_golden(hadi, ctx):
     """BASELINE config 4 at full size: European call, 400 x 200 x 200.  Golden prices from the reference's
     own code (SURVEY.md 8(c) probe): Craig-Sneyd host solver and device Douglas path."""
