@@ -38,6 +38,27 @@ constexpr int kCh = 4;   // nodes per register chunk of a chain
 
 __device__ __forceinline__ double wld(const double* p) { return __ldcg(p); }
 
+// ---- per-stage cycle counters (HADI_PHASE_TIMING builds; thread 0 of every CTA, read with hadi_batch_prof_raw) ----------
+// [0] set-up  [1] team barriers  [2] right-hand sides of the A1 sweeps  [3] A1 chains  [4] A2 chains
+// [5] right-hand sides of the A2 sweeps  [6] solutions back to global memory (+ projection)  [7] factor reloads
+struct WideProf {
+#ifdef HADI_PHASE_TIMING
+  long long* p;
+  long long t;
+#endif
+};
+__device__ __forceinline__ void wide_tick(WideProf& pf, int k, int tid) {
+#ifdef HADI_PHASE_TIMING
+  if (tid == 0 && pf.p != nullptr) {
+    const long long now = clock64();
+    pf.p[k] += now - pf.t;
+    pf.t = now;
+  }
+#else
+  (void)pf; (void)k; (void)tid;
+#endif
+}
+
 // ---- team barrier ------------------------------------------------------------------------------------------------
 struct WideTeam {
   unsigned* ctr;    // monotonic arrival counter of the team (zeroed by the host before the launch)
@@ -215,26 +236,28 @@ __device__ __forceinline__ double wide_node_correct(const HadiItem& it, const Ha
 }
 
 // ---- the chains: one thread per line, every operand in shared memory, next chunk's operands in flight --------------------
+// The chain of a chunk is straight-line code: whole chunks only (nodes past the end of a line compute on the padding of
+// the line buffers and are never stored over live data), and the guarded division raises a flag instead of branching;
+// a chunk whose flag is up (operands below 2^-900 in the far out-of-the-money corner of a large grid) is redone with
+// the IEEE division from the saved entry value — same bits as dividing in line, without a branch per node on the chain.
 // A1 (hadi_phase_solve_a1): forward x_i = y_i - m_i x_{i-1}; back x_i = (x_i - impl_upper_i x_{i+1}) / pivot_i
 __device__ __forceinline__ void wide_chain_a1(double* __restrict__ y, double* __restrict__ d, const double* __restrict__ m,
                                               const double* __restrict__ tb, const double* __restrict__ iu, int m1) {
-  unsigned bad = 0;
   double x = y[0];
   d[0] = x;
   {
     double yy[kCh], mm[kCh];
 #pragma unroll
     for (int k = 0; k < kCh; ++k) { yy[k] = y[1 + k]; mm[k] = m[k]; }
+#pragma unroll 1
     for (int ib = 1; ib <= m1; ib += kCh) {
       double ny[kCh], nm[kCh];
 #pragma unroll
       for (int k = 0; k < kCh; ++k) { ny[k] = y[ib + kCh + k]; nm[k] = m[ib + kCh - 1 + k]; }   // buffers are padded by 2 chunks
 #pragma unroll
       for (int k = 0; k < kCh; ++k) {
-        if (ib + k <= m1) {
-          x = yy[k] - mm[k] * x;
-          d[ib + k] = x;
-        }
+        x = yy[k] - mm[k] * x;
+        d[ib + k] = x;
       }
 #pragma unroll
       for (int k = 0; k < kCh; ++k) { yy[k] = ny[k]; mm[k] = nm[k]; }
@@ -249,6 +272,7 @@ __device__ __forceinline__ void wide_chain_a1(double* __restrict__ y, double* __
       const int i = (m1 - k >= 1) ? m1 - k : 1;
       tt[k] = tb[2 * k]; rr[k] = tb[2 * k + 1]; dd[k] = d[i]; uu[k] = iu[i];
     }
+#pragma unroll 1
     for (int kb = 0; kb < m1; kb += kCh) {
       double nt[kCh], nr[kCh], nd[kCh], nu[kCh];
 #pragma unroll
@@ -257,15 +281,28 @@ __device__ __forceinline__ void wide_chain_a1(double* __restrict__ y, double* __
         const int i = (m1 - kk >= 1) ? m1 - kk : 1;
         nt[k] = tb[2 * kk]; nr[k] = tb[2 * kk + 1]; nd[k] = d[i]; nu[k] = iu[i];
       }
+      const double x_in = xn;
+      const int live = m1 - kb;   // nodes of this chunk that exist: k < live
+      double xo[kCh];
+      unsigned bad = 0;
 #pragma unroll
       for (int k = 0; k < kCh; ++k) {
-        const int i = m1 - kb - k;
-        if (i >= 1) {
-          x = hadi_div<false, true>(dd[k] - uu[k] * xn, tt[k], rr[k], bad);
-          xn = x;
-          y[i] = x;
+        unsigned b1 = 0;
+        xn = hadi_div<false, false>(dd[k] - uu[k] * xn, tt[k], rr[k], b1);
+        xo[k] = xn;
+        bad |= (k < live) ? b1 : 0u;
+      }
+      if (bad != 0u) {
+        xn = x_in;
+#pragma unroll
+        for (int k = 0; k < kCh; ++k) {
+          xn = (dd[k] - uu[k] * xn) / tt[k];
+          xo[k] = xn;
         }
       }
+#pragma unroll
+      for (int k = 0; k < kCh; ++k)
+        if (k < live) y[m1 - kb - k] = xo[k];
 #pragma unroll
       for (int k = 0; k < kCh; ++k) { tt[k] = nt[k]; rr[k] = nr[k]; dd[k] = nd[k]; uu[k] = nu[k]; }
     }
@@ -287,6 +324,7 @@ __device__ __forceinline__ void wide_chain_a2(double* __restrict__ b, double* __
       const int j = (1 + k <= m2) ? 1 + k : m2;
       bb[k] = b[j]; ff[k] = F[j]; gg[k] = G[j]; mm[k] = MM[j];
     }
+#pragma unroll 1
     for (int jb = 1; jb <= m2; jb += kCh) {
       double nb[kCh], nf[kCh], ng[kCh], nm[kCh];
 #pragma unroll
@@ -296,12 +334,10 @@ __device__ __forceinline__ void wide_chain_a2(double* __restrict__ b, double* __
       }
 #pragma unroll
       for (int k = 0; k < kCh; ++k) {
-        if (jb + k <= m2) {
-          const double v = (bb[k] - ff[k] * d1 - gg[k] * d2) * mm[k];
-          d[jb + k] = v;
-          d2 = d1;
-          d1 = v;
-        }
+        const double v = (bb[k] - ff[k] * d1 - gg[k] * d2) * mm[k];
+        d[jb + k] = v;   // rows past m2 land in the padding of the column buffer
+        d2 = d1;
+        d1 = v;
       }
 #pragma unroll
       for (int k = 0; k < kCh; ++k) { bb[k] = nb[k]; ff[k] = nf[k]; gg[k] = ng[k]; mm[k] = nm[k]; }
@@ -315,6 +351,7 @@ __device__ __forceinline__ void wide_chain_a2(double* __restrict__ b, double* __
       const int j = (m2 - k >= 0) ? m2 - k : 0;
       dd[k] = d[j]; cc[k] = CP[j]; c2[k] = C2P[j];
     }
+#pragma unroll 1
     for (int jt = m2; jt >= 0; jt -= kCh) {
       double nd[kCh], nc[kCh], n2[kCh];
 #pragma unroll
@@ -324,12 +361,10 @@ __device__ __forceinline__ void wide_chain_a2(double* __restrict__ b, double* __
       }
 #pragma unroll
       for (int k = 0; k < kCh; ++k) {
-        if (jt - k >= 0) {
-          const double x = dd[k] - cc[k] * x1 - c2[k] * x2;
-          x2 = x1;
-          x1 = x;
-          b[jt - k] = x;
-        }
+        const double x = dd[k] - cc[k] * x1 - c2[k] * x2;
+        x2 = x1;
+        x1 = x;
+        if (jt - k >= 0) b[jt - k] = x;
       }
 #pragma unroll
       for (int k = 0; k < kCh; ++k) { dd[k] = nd[k]; cc[k] = nc[k]; c2[k] = n2[k]; }
@@ -363,12 +398,13 @@ __device__ __forceinline__ void wide_load_factors(const HadiItem& it, const Hadi
 // kind: 0 Douglas explicit stage, 1 Craig-Sneyd-family predictor, 2 corrector
 template <int KIND>
 __device__ __forceinline__ void wide_rows(const HadiItem& it, const HadiView& w, const HadiCsView& cs, const WideGeo& g,
-                                          double e0, double e1, int scheme, int tid) {
+                                          double e0, double e1, int scheme, int tid, WideProf& pf) {
   const int m1 = w.m1, nc = m1 + 1;
   for (int b0 = 0; b0 < g.nrow; b0 += g.RB) {
     const int nb = min(g.RB, g.nrow - b0);
     if (!g.resident)
       for (int r = 0; r < nb; ++r) wide_load_factors(it, w, g, r, g.rank + g.G * (b0 + r), tid);
+    wide_tick(pf, 7, tid);
     for (int idx = tid; idx < nb * nc; idx += kWideThreads) {
       const int r = idx / nc, i = idx - r * nc;
       const int j = g.rank + g.G * (b0 + r);
@@ -379,18 +415,21 @@ __device__ __forceinline__ void wide_rows(const HadiItem& it, const HadiView& w,
       g.ry[r * g.pr + i] = rhs;
     }
     __syncthreads();
+    wide_tick(pf, 2, tid);
     {
       const int r = wide_line_of_thread(tid);
       if (r < nb)
         wide_chain_a1(g.ry + r * g.pr, g.rd + r * g.pr, g.rm + r * g.pr, g.rt + r * 2 * g.pr, g.ru + r * g.pr, m1);
     }
     __syncthreads();
+    wide_tick(pf, 3, tid);
     for (int idx = tid; idx < nb * nc; idx += kWideThreads) {
       const int r = idx / nc, i = idx - r * nc;
       const int j = g.rank + g.G * (b0 + r);
       w.Y[j * w.ld + i] = g.ry[r * g.pr + i];
     }
     if (b0 + g.RB < g.nrow) __syncthreads();
+    wide_tick(pf, 6, tid);
   }
 }
 
@@ -398,7 +437,7 @@ __device__ __forceinline__ void wide_rows(const HadiItem& it, const HadiView& w,
 // the Dirichlet column of the put boundary set and the American projection follow the sweep (hadi_phase_project);
 // otherwise the right-hand side takes the stored R2 (hadi_cs_rhs2).
 __device__ __forceinline__ void wide_cols(const HadiItem& it, const HadiView& w, const HadiCsView& cs, const WideGeo& g,
-                                          double e0, double e1, bool douglas, double g_dir, double rdt, int tid) {
+                                          double e0, double e1, bool douglas, double g_dir, double rdt, int tid, WideProf& pf) {
   const int m2 = w.m2, ld = w.ld, n2 = w.n2, nr = m2 + 1;
   const double c = w.c, dt = it.dt;
   const bool am = douglas && it.style == 1;
@@ -427,6 +466,7 @@ __device__ __forceinline__ void wide_cols(const HadiItem& it, const HadiView& w,
       g.cb[cc * g.pc + j] = v;
     }
     __syncthreads();
+    wide_tick(pf, 5, tid);
     {
       const int cc = wide_line_of_thread(tid);
       if (cc < nb)
@@ -434,6 +474,7 @@ __device__ __forceinline__ void wide_cols(const HadiItem& it, const HadiView& w,
                       tj + TJ_C2P * n2, m2);
     }
     __syncthreads();
+    wide_tick(pf, 4, tid);
     for (int idx = tid; idx < nb * nr; idx += kWideThreads) {
       const int j = idx / nb, cc = idx - j * nb;
       const int i = g.c0 + b0 + cc;
@@ -451,6 +492,7 @@ __device__ __forceinline__ void wide_cols(const HadiItem& it, const HadiView& w,
       w.U[q] = x;
     }
     if (b0 + g.CB < g.ncol) __syncthreads();
+    wide_tick(pf, 6, tid);
   }
 }
 
@@ -517,6 +559,11 @@ __global__ void __launch_bounds__(kWideThreads, 1) hadi_wide_kernel(const HadiLa
   const int gtid = rank * kWideThreads + tid, gnt = G * kWideThreads;
   for (int k = gtid; k < (m2 + 1 + 2 * HADI_HALO) * w.ld + 2; k += gnt) Ualloc[k] = 0.0;
 
+  WideProf pf;
+#ifdef HADI_PHASE_TIMING
+  pf.p = L.prof ? L.prof + 8 * (size_t)blockIdx.x : nullptr;
+  pf.t = clock64();
+#endif
   for (int item = team; item < L.n_items; item += n_teams) {
     const HadiItem it = L.items[item];
     const double* sg = L.s_pool + it.s_off;
@@ -543,23 +590,31 @@ __global__ void __launch_bounds__(kWideThreads, 1) hadi_wide_kernel(const HadiLa
     }
     if (g.resident)
       for (int r = 0; r < g.nrow; ++r) wide_load_factors(it, w, g, r, rank + G * r, tid);
+    wide_tick(pf, 0, tid);
     wide_sync(tm, tid);
+    wide_tick(pf, 1, tid);
     for (int n = 1; n <= it.N; ++n) {
       const double e0 = eg[n - 1], e1 = eg[n];
       if (L.scheme >= 1) {
-        wide_rows<1>(it, w, cs, g, e0, e1, L.scheme, tid);
+        wide_rows<1>(it, w, cs, g, e0, e1, L.scheme, tid, pf);
         wide_sync(tm, tid);
-        wide_cols(it, w, cs, g, e0, e1, false, 0.0, rdt, tid);   // Y2 -> U
+        wide_tick(pf, 1, tid);
+        wide_cols(it, w, cs, g, e0, e1, false, 0.0, rdt, tid, pf);   // Y2 -> U
         wide_sync(tm, tid);
-        wide_rows<2>(it, w, cs, g, e0, e1, L.scheme, tid);
+        wide_tick(pf, 1, tid);
+        wide_rows<2>(it, w, cs, g, e0, e1, L.scheme, tid, pf);
         wide_sync(tm, tid);
-        wide_cols(it, w, cs, g, L.scheme == HADI_SCHEME_HV ? e1 : e0, e1, false, 0.0, rdt, tid);
+        wide_tick(pf, 1, tid);
+        wide_cols(it, w, cs, g, L.scheme == HADI_SCHEME_HV ? e1 : e0, e1, false, 0.0, rdt, tid, pf);
         wide_sync(tm, tid);
+        wide_tick(pf, 1, tid);
       } else {
-        wide_rows<0>(it, w, cs, g, e0, e1, 0, tid);
+        wide_rows<0>(it, w, cs, g, e0, e1, 0, tid, pf);
         wide_sync(tm, tid);
-        wide_cols(it, w, cs, g, e0, e1, true, it.bc ? it.K * eg[it.N + 1 + n] : 0.0, rdt, tid);
+        wide_tick(pf, 1, tid);
+        wide_cols(it, w, cs, g, e0, e1, true, it.bc ? it.K * eg[it.N + 1 + n] : 0.0, rdt, tid, pf);
         wide_sync(tm, tid);
+        wide_tick(pf, 1, tid);
       }
     }
     if (gtid == 0) {

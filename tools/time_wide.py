@@ -21,7 +21,7 @@ def run(m1, m2, scheme, nopt, N):
     return min(ts), v
 for (m1, m2, N) in ((400, 200, steps), (100, 50, 50)):
     for scheme, name in ((hadi.CRAIG_SNEYD, "CS"), (hadi.DOUGLAS, "DO")):
-        for nopt in (1, 2, 4, 8, 18, 37, 74, 148):
+        for nopt in ((1, 4, 8, 18, 37) if os.environ.get("WIDE_QUICK") else (1, 2, 4, 8, 18, 37, 74, 148)):
             os.environ.pop("HADI_FORCE_VARIANT", None)
             os.environ["HADI_WIDE_MAX_ITEMS"] = "0"
             t0, v0 = run(m1, m2, scheme, nopt, N)
