@@ -35,6 +35,7 @@ namespace {
 constexpr int kWideThreads = 512;
 constexpr int kWideWarps = kWideThreads / 32;
 constexpr int kCh = 4;   // nodes per register chunk of a chain
+constexpr int kPad = 2 * kCh;   // the sweeps are unrolled by two chunks and prefetch one chunk ahead
 
 __device__ __forceinline__ double wld(const double* p) { return __ldcg(p); }
 
@@ -86,11 +87,15 @@ struct WideGeo {
   int nrow;          // owned rows: rank + G*k, k < nrow
   int c0, ncol;      // owned columns [c0, c0 + ncol)
   int RB, CB;        // lines per batch
-  int pr, pc;        // pitches (doubles) of a row / column buffer
+  int pr, pc;        // entries per row buffer (pairs) / per column buffer (doubles), padding included
   bool resident;     // every owned row fits one batch: its A1 factors are loaded once per solve
-  double *ry, *rd, *rm, *rt, *ru;   // [RB][pr] right-hand side -> solution | forward result | multipliers |
-                                    // [RB][2*pr] pivot, prepared reciprocal (back-substitution order) | impl_upper
-  double *cb, *cd, *cl;             // [CB][pc] right-hand side -> solution | forward result | lambda
+  // Row buffers, [RB][pr] pairs each, node i / element k at entry kPad + i: the chains run whole chunks and may touch
+  // kPad entries either side of a line.
+  double2 *rA;       // {right-hand side -> solution, Thomas multiplier m_i}
+  double2 *rB;       // {forward result d_i, impl_upper_i}
+  double2 *rC;       // element k of the back substitution (node m1 - k): {pivot, prepared reciprocal}
+  double *cb, *cd, *cl;   // [CB][pc] right-hand side -> solution | forward result | lambda; row j at entry kPad + j
+  double* t2;        // [n2 + 2 kPad][6] A2 factor records {F, G, MM, -, CP, C2P}, row j at record kPad + j
 };
 
 // the 11 neighbours of node (j, i) the explicit operators need
@@ -237,137 +242,150 @@ __device__ __forceinline__ double wide_node_correct(const HadiItem& it, const Ha
 
 // ---- the chains: one thread per line, every operand in shared memory, next chunk's operands in flight --------------------
 // The chain of a chunk is straight-line code: whole chunks only (nodes past the end of a line compute on the padding of
-// the line buffers and are never stored over live data), and the guarded division raises a flag instead of branching;
-// a chunk whose flag is up (operands below 2^-900 in the far out-of-the-money corner of a large grid) is redone with
-// the IEEE division from the saved entry value — same bits as dividing in line, without a branch per node on the chain.
+// the line buffers), operands arrive as 16-byte pairs, two chunk bodies per loop trip swap their register sets instead
+// of copying them, and the guarded division raises a flag instead of branching; a chunk whose flag is up (operands
+// below 2^-900 in the far out-of-the-money corner of a large grid) is redone with the IEEE division from the saved
+// entry value — the same bits as dividing in line, without a branch per node on the chain.
 // A1 (hadi_phase_solve_a1): forward x_i = y_i - m_i x_{i-1}; back x_i = (x_i - impl_upper_i x_{i+1}) / pivot_i
-__device__ __forceinline__ void wide_chain_a1(double* __restrict__ y, double* __restrict__ d, const double* __restrict__ m,
-                                              const double* __restrict__ tb, const double* __restrict__ iu, int m1) {
-  double x = y[0];
-  d[0] = x;
+struct WideA1Fwd { double2 v[kCh]; };
+struct WideA1Bwd { double2 c[kCh], b[kCh]; };
+__device__ __forceinline__ void wide_a1_fwd_chunk(const WideA1Fwd& cur, WideA1Fwd& nxt, const double2* __restrict__ A,
+                                                  double2* __restrict__ B, int ib, double& x) {
+#pragma unroll
+  for (int k = 0; k < kCh; ++k) nxt.v[k] = A[ib + kCh + k];
+#pragma unroll
+  for (int k = 0; k < kCh; ++k) {
+    x = cur.v[k].x - cur.v[k].y * x;
+    B[ib + k].x = x;
+  }
+}
+__device__ __forceinline__ void wide_a1_bwd_chunk(const WideA1Bwd& cur, WideA1Bwd& nxt, double2* __restrict__ A,
+                                                  const double2* __restrict__ B, const double2* __restrict__ C, int m1, int kb,
+                                                  double& xn) {
+#pragma unroll
+  for (int k = 0; k < kCh; ++k) {
+    nxt.c[k] = C[kb + kCh + k];
+    nxt.b[k] = B[m1 - (kb + kCh + k)];
+  }
+  const double x_in = xn;
+  double xo[kCh];
+  unsigned bad = 0;
+#pragma unroll
+  for (int k = 0; k < kCh; ++k) {
+    xn = hadi_div<false, false>(cur.b[k].x - cur.b[k].y * xn, cur.c[k].x, cur.c[k].y, bad);
+    xo[k] = xn;
+  }
+  if (bad != 0u) {
+    xn = x_in;
+#pragma unroll
+    for (int k = 0; k < kCh; ++k) {
+      xn = (cur.b[k].x - cur.b[k].y * xn) / cur.c[k].x;
+      xo[k] = xn;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kCh; ++k) A[m1 - kb - k].x = xo[k];
+}
+// A, B, C point at node 0 / element 0 of the line (kPad entries of padding either side)
+__device__ __forceinline__ void wide_chain_a1(double2* __restrict__ A, double2* __restrict__ B, const double2* __restrict__ C,
+                                              int m1) {
+  double x = A[0].x;
+  B[0].x = x;
   {
-    double yy[kCh], mm[kCh];
+    WideA1Fwd p, q;
 #pragma unroll
-    for (int k = 0; k < kCh; ++k) { yy[k] = y[1 + k]; mm[k] = m[k]; }
+    for (int k = 0; k < kCh; ++k) p.v[k] = A[1 + k];
 #pragma unroll 1
-    for (int ib = 1; ib <= m1; ib += kCh) {
-      double ny[kCh], nm[kCh];
-#pragma unroll
-      for (int k = 0; k < kCh; ++k) { ny[k] = y[ib + kCh + k]; nm[k] = m[ib + kCh - 1 + k]; }   // buffers are padded by 2 chunks
-#pragma unroll
-      for (int k = 0; k < kCh; ++k) {
-        x = yy[k] - mm[k] * x;
-        d[ib + k] = x;
-      }
-#pragma unroll
-      for (int k = 0; k < kCh; ++k) { yy[k] = ny[k]; mm[k] = nm[k]; }
+    for (int ib = 1; ib <= m1; ib += 2 * kCh) {
+      wide_a1_fwd_chunk(p, q, A, B, ib, x);
+      wide_a1_fwd_chunk(q, p, A, B, ib + kCh, x);
     }
   }
   double xn = 0.0;
   {
     // element k of the back-substitution order is node i = m1 - k
-    double tt[kCh], rr[kCh], dd[kCh], uu[kCh];
+    WideA1Bwd p, q;
 #pragma unroll
-    for (int k = 0; k < kCh; ++k) {
-      const int i = (m1 - k >= 1) ? m1 - k : 1;
-      tt[k] = tb[2 * k]; rr[k] = tb[2 * k + 1]; dd[k] = d[i]; uu[k] = iu[i];
-    }
+    for (int k = 0; k < kCh; ++k) { p.c[k] = C[k]; p.b[k] = B[m1 - k]; }
 #pragma unroll 1
-    for (int kb = 0; kb < m1; kb += kCh) {
-      double nt[kCh], nr[kCh], nd[kCh], nu[kCh];
-#pragma unroll
-      for (int k = 0; k < kCh; ++k) {
-        const int kk = kb + kCh + k;
-        const int i = (m1 - kk >= 1) ? m1 - kk : 1;
-        nt[k] = tb[2 * kk]; nr[k] = tb[2 * kk + 1]; nd[k] = d[i]; nu[k] = iu[i];
-      }
-      const double x_in = xn;
-      const int live = m1 - kb;   // nodes of this chunk that exist: k < live
-      double xo[kCh];
-      unsigned bad = 0;
-#pragma unroll
-      for (int k = 0; k < kCh; ++k) {
-        unsigned b1 = 0;
-        xn = hadi_div<false, false>(dd[k] - uu[k] * xn, tt[k], rr[k], b1);
-        xo[k] = xn;
-        bad |= (k < live) ? b1 : 0u;
-      }
-      if (bad != 0u) {
-        xn = x_in;
-#pragma unroll
-        for (int k = 0; k < kCh; ++k) {
-          xn = (dd[k] - uu[k] * xn) / tt[k];
-          xo[k] = xn;
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < kCh; ++k)
-        if (k < live) y[m1 - kb - k] = xo[k];
-#pragma unroll
-      for (int k = 0; k < kCh; ++k) { tt[k] = nt[k]; rr[k] = nr[k]; dd[k] = nd[k]; uu[k] = nu[k]; }
+    for (int kb = 0; kb < m1; kb += 2 * kCh) {
+      wide_a1_bwd_chunk(p, q, A, B, C, m1, kb, xn);
+      wide_a1_bwd_chunk(q, p, A, B, C, m1, kb + kCh, xn);
     }
   }
-  y[0] = d[0];
+  A[0].x = B[0].x;
 }
 // A2 (hadi_phase_solve_a2): d_j = (b_j - f_j d_{j-1} - g_j d_{j-2}) m_j; x_j = d_j - c'_j x_{j+1} - c2'_j x_{j+2}
-__device__ __forceinline__ void wide_chain_a2(double* __restrict__ b, double* __restrict__ d, const double* __restrict__ F,
-                                              const double* __restrict__ G, const double* __restrict__ MM,
-                                              const double* __restrict__ CP, const double* __restrict__ C2P, int m2) {
+// T: factor records {F, G, MM, -, CP, C2P} of row 0 (kPad records of padding either side); b, d: row 0 of the column
+struct WideA2Fwd { double b[kCh], mm[kCh]; double2 fg[kCh]; };
+struct WideA2Bwd { double d[kCh]; double2 cc[kCh]; };
+__device__ __forceinline__ void wide_a2_fwd_chunk(const WideA2Fwd& cur, WideA2Fwd& nxt, const double* __restrict__ b,
+                                                  double* __restrict__ d, const double* __restrict__ T, int jb, double& d1,
+                                                  double& d2) {
+#pragma unroll
+  for (int k = 0; k < kCh; ++k) {
+    const int j = jb + kCh + k;
+    nxt.b[k] = b[j];
+    nxt.fg[k] = *reinterpret_cast<const double2*>(T + 6 * j);
+    nxt.mm[k] = T[6 * j + 2];
+  }
+#pragma unroll
+  for (int k = 0; k < kCh; ++k) {
+    const double v = (cur.b[k] - cur.fg[k].x * d1 - cur.fg[k].y * d2) * cur.mm[k];
+    d[jb + k] = v;
+    d2 = d1;
+    d1 = v;
+  }
+}
+__device__ __forceinline__ void wide_a2_bwd_chunk(const WideA2Bwd& cur, WideA2Bwd& nxt, double* __restrict__ b,
+                                                  const double* __restrict__ d, const double* __restrict__ T, int jt, double& x1,
+                                                  double& x2) {
+#pragma unroll
+  for (int k = 0; k < kCh; ++k) {
+    const int j = jt - kCh - k;
+    nxt.d[k] = d[j];
+    nxt.cc[k] = *reinterpret_cast<const double2*>(T + 6 * j + 4);
+  }
+#pragma unroll
+  for (int k = 0; k < kCh; ++k) {
+    const double x = cur.d[k] - cur.cc[k].x * x1 - cur.cc[k].y * x2;
+    x2 = x1;
+    x1 = x;
+    b[jt - k] = x;
+  }
+}
+__device__ __forceinline__ void wide_chain_a2(double* __restrict__ b, double* __restrict__ d, const double* __restrict__ T,
+                                              const double* __restrict__ tj, int n2, int m2) {
   unsigned bad = 0;
-  double d1 = hadi_div<false, true>(b[0], MM[0], G[0], bad);
+  double d1 = hadi_div<false, true>(b[0], tj[TJ_MM * n2], tj[TJ_G * n2], bad);
   double d2 = 0.0;
   d[0] = d1;
   {
-    double bb[kCh], ff[kCh], gg[kCh], mm[kCh];
+    WideA2Fwd p, q;
 #pragma unroll
     for (int k = 0; k < kCh; ++k) {
-      const int j = (1 + k <= m2) ? 1 + k : m2;
-      bb[k] = b[j]; ff[k] = F[j]; gg[k] = G[j]; mm[k] = MM[j];
+      p.b[k] = b[1 + k];
+      p.fg[k] = *reinterpret_cast<const double2*>(T + 6 * (1 + k));
+      p.mm[k] = T[6 * (1 + k) + 2];
     }
 #pragma unroll 1
-    for (int jb = 1; jb <= m2; jb += kCh) {
-      double nb[kCh], nf[kCh], ng[kCh], nm[kCh];
-#pragma unroll
-      for (int k = 0; k < kCh; ++k) {
-        const int j = (jb + kCh + k <= m2) ? jb + kCh + k : m2;
-        nb[k] = b[j]; nf[k] = F[j]; ng[k] = G[j]; nm[k] = MM[j];
-      }
-#pragma unroll
-      for (int k = 0; k < kCh; ++k) {
-        const double v = (bb[k] - ff[k] * d1 - gg[k] * d2) * mm[k];
-        d[jb + k] = v;   // rows past m2 land in the padding of the column buffer
-        d2 = d1;
-        d1 = v;
-      }
-#pragma unroll
-      for (int k = 0; k < kCh; ++k) { bb[k] = nb[k]; ff[k] = nf[k]; gg[k] = ng[k]; mm[k] = nm[k]; }
+    for (int jb = 1; jb <= m2; jb += 2 * kCh) {
+      wide_a2_fwd_chunk(p, q, b, d, T, jb, d1, d2);
+      wide_a2_fwd_chunk(q, p, b, d, T, jb + kCh, d1, d2);
     }
   }
   double x1 = 0.0, x2 = 0.0;
   {
-    double dd[kCh], cc[kCh], c2[kCh];
+    WideA2Bwd p, q;
 #pragma unroll
     for (int k = 0; k < kCh; ++k) {
-      const int j = (m2 - k >= 0) ? m2 - k : 0;
-      dd[k] = d[j]; cc[k] = CP[j]; c2[k] = C2P[j];
+      p.d[k] = d[m2 - k];
+      p.cc[k] = *reinterpret_cast<const double2*>(T + 6 * (m2 - k) + 4);
     }
 #pragma unroll 1
-    for (int jt = m2; jt >= 0; jt -= kCh) {
-      double nd[kCh], nc[kCh], n2[kCh];
-#pragma unroll
-      for (int k = 0; k < kCh; ++k) {
-        const int j = (jt - kCh - k >= 0) ? jt - kCh - k : 0;
-        nd[k] = d[j]; nc[k] = CP[j]; n2[k] = C2P[j];
-      }
-#pragma unroll
-      for (int k = 0; k < kCh; ++k) {
-        const double x = dd[k] - cc[k] * x1 - c2[k] * x2;
-        x2 = x1;
-        x1 = x;
-        if (jt - k >= 0) b[jt - k] = x;
-      }
-#pragma unroll
-      for (int k = 0; k < kCh; ++k) { dd[k] = nd[k]; cc[k] = nc[k]; c2[k] = n2[k]; }
+    for (int jt = m2; jt >= 0; jt -= 2 * kCh) {
+      wide_a2_bwd_chunk(p, q, b, d, T, jt, x1, x2);
+      wide_a2_bwd_chunk(q, p, b, d, T, jt - kCh, x1, x2);
     }
   }
 }
@@ -384,14 +402,13 @@ __device__ __forceinline__ void wide_load_factors(const HadiItem& it, const Hadi
   const double vj = w.tj[TJ_V * w.n2 + j];
   const double theta = it.theta, dt = it.dt;
   for (int k = tid; k < m1; k += kWideThreads) {
-    g.rm[r * g.pr + k] = wld(fM + k);
-    g.rt[r * 2 * g.pr + 2 * k] = wld(fB + 2 * k);
-    g.rt[r * 2 * g.pr + 2 * k + 1] = wld(fB + 2 * k + 1);
+    g.rA[r * g.pr + kPad + 1 + k].y = wld(fM + k);   // node i = k + 1 takes multiplier m_i
+    g.rC[r * g.pr + kPad + k] = make_double2(wld(fB + 2 * k), wld(fB + 2 * k + 1));
   }
   for (int i = tid; i <= m1; i += kWideThreads) {
     const double a = hadi_ti(w, TI_HS2)[i] * vj;
     const double up = a * hadi_ti(w, TI_DSP)[i] + hadi_ti(w, TI_BBP)[i];
-    g.ru[r * g.pr + i] = -theta * dt * up;
+    g.rB[r * g.pr + kPad + i].y = -theta * dt * up;
   }
 }
 
@@ -412,21 +429,21 @@ __device__ __forceinline__ void wide_rows(const HadiItem& it, const HadiView& w,
       if (KIND == 0) rhs = wide_node_explicit(it, w, e0, e1, i, j);
       else if (KIND == 1) rhs = wide_node_predict(it, w, cs, e0, e1, i, j, scheme);
       else rhs = wide_node_correct(it, w, cs, e0, e1, i, j, scheme);
-      g.ry[r * g.pr + i] = rhs;
+      g.rA[r * g.pr + kPad + i].x = rhs;
     }
     __syncthreads();
     wide_tick(pf, 2, tid);
     {
       const int r = wide_line_of_thread(tid);
       if (r < nb)
-        wide_chain_a1(g.ry + r * g.pr, g.rd + r * g.pr, g.rm + r * g.pr, g.rt + r * 2 * g.pr, g.ru + r * g.pr, m1);
+        wide_chain_a1(g.rA + r * g.pr + kPad, g.rB + r * g.pr + kPad, g.rC + r * g.pr + kPad, m1);
     }
     __syncthreads();
     wide_tick(pf, 3, tid);
     for (int idx = tid; idx < nb * nc; idx += kWideThreads) {
       const int r = idx / nc, i = idx - r * nc;
       const int j = g.rank + g.G * (b0 + r);
-      w.Y[j * w.ld + i] = g.ry[r * g.pr + i];
+      w.Y[j * w.ld + i] = g.rA[r * g.pr + kPad + i].x;
     }
     if (b0 + g.RB < g.nrow) __syncthreads();
     wide_tick(pf, 6, tid);
@@ -457,21 +474,20 @@ __device__ __forceinline__ void wide_cols(const HadiItem& it, const HadiView& w,
         r2 += tj[TJ_U2 * n2 + j] * wld(p + 2 * ld);
         const double b2 = (j == m2) ? hadi_ti(w, TI_B2V)[i] : 0.0;
         v = y + c * (b2 * e1 - (r2 + b2 * e0));
-        if (am) g.cl[cc * g.pc + j] = wld(w.lam + q);
+        if (am) g.cl[cc * g.pc + kPad + j] = wld(w.lam + q);
       } else {
         double b1p, b2p;
         hadi_cs_bounds(it, w, i, j, b1p, b2p);
         v = y + c * (b2p * e1 - (wld(cs.R2 + q) + b2p * e0));
       }
-      g.cb[cc * g.pc + j] = v;
+      g.cb[cc * g.pc + kPad + j] = v;
     }
     __syncthreads();
     wide_tick(pf, 5, tid);
     {
       const int cc = wide_line_of_thread(tid);
       if (cc < nb)
-        wide_chain_a2(g.cb + cc * g.pc, g.cd + cc * g.pc, tj + TJ_F * n2, tj + TJ_G * n2, tj + TJ_MM * n2, tj + TJ_CP * n2,
-                      tj + TJ_C2P * n2, m2);
+        wide_chain_a2(g.cb + cc * g.pc + kPad, g.cd + cc * g.pc + kPad, g.t2 + 6 * kPad, tj, n2, m2);
     }
     __syncthreads();
     wide_tick(pf, 4, tid);
@@ -479,12 +495,12 @@ __device__ __forceinline__ void wide_cols(const HadiItem& it, const HadiView& w,
       const int j = idx / nb, cc = idx - j * nb;
       const int i = g.c0 + b0 + cc;
       const int q = j * ld + i;
-      double x = g.cb[cc * g.pc + j];
+      double x = g.cb[cc * g.pc + kPad + j];
       if (douglas && it.bc && i == 0) x = g_dir;
       if (am) {
         unsigned bad = 0;
         const double u0 = hadi_ti(w, TI_PAY)[i];
-        const double l = g.cl[cc * g.pc + j];
+        const double l = g.cl[cc * g.pc + kPad + j];
         const double ln = hadi_max(0.0, l + hadi_div<false, true>(u0 - x, dt, rdt, bad));
         w.lam[q] = (i == w.m1) ? 0.0 : ln;
         x = hadi_max(x - dt * l, u0);
@@ -497,7 +513,7 @@ __device__ __forceinline__ void wide_cols(const HadiItem& it, const HadiView& w,
 }
 
 __global__ void __launch_bounds__(kWideThreads, 1) hadi_wide_kernel(const HadiLaunch L, const int G) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x;
   const int team = blockIdx.x / G, rank = blockIdx.x - team * G, n_teams = gridDim.x / G;
   const int m1 = L.m1, m2 = L.m2;
@@ -529,28 +545,29 @@ __global__ void __launch_bounds__(kWideThreads, 1) hadi_wide_kernel(const HadiLa
   g.nrow = (rank <= m2) ? (m2 - rank) / G + 1 : 0;
   g.c0 = (int)(((long long)rank * (m1 + 1)) / G);
   g.ncol = (int)(((long long)(rank + 1) * (m1 + 1)) / G) - g.c0;
-  g.pr = w.n1 + 2 * kCh;
-  g.pc = (w.n2 + 2 * kCh) | 1;
+  // arena: A2 factor records | row buffers | column buffers (behind the row buffers when those stay resident)
+  g.t2 = arena;
+  const int t2_doubles = 6 * (w.n2 + 2 * kPad);
+  double* lines = arena + t2_doubles;
+  const int line_doubles = arena_doubles - t2_doubles;
+  g.pr = w.n1 + 2 * kPad;
+  g.pc = (w.n2 + 2 * kPad) | 1;
   const int max_row = (m2 + G) / G, max_col = (m1 + G) / G;
-  g.RB = min(max_row, arena_doubles / (6 * g.pr));
-  g.CB = min(max_col, arena_doubles / (3 * g.pc));
+  g.RB = min(max_row, line_doubles / (6 * g.pr));
+  g.CB = min(max_col, line_doubles / (3 * g.pc));
   g.resident = max_row <= g.RB;
-  g.ry = arena;
-  g.rd = g.ry + (size_t)g.RB * g.pr;
-  g.rm = g.rd + (size_t)g.RB * g.pr;
-  g.ru = g.rm + (size_t)g.RB * g.pr;
-  g.rt = g.ru + (size_t)g.RB * g.pr;
-  g.cb = arena;
-  g.cd = g.cb + (size_t)g.CB * g.pc;
-  g.cl = g.cd + (size_t)g.CB * g.pc;
+  g.rA = reinterpret_cast<double2*>(lines);
+  g.rB = g.rA + (size_t)g.RB * g.pr;
+  g.rC = g.rB + (size_t)g.RB * g.pr;
+  g.cb = lines;
   // the row buffers of a resident team member hold its factors for the whole solve: the column buffers then sit behind them
   if (g.resident) {
     const int used = 6 * g.RB * g.pr;
-    g.CB = min(max_col, (arena_doubles - used) / (3 * g.pc));
-    g.cb = arena + used;
-    g.cd = g.cb + (size_t)g.CB * g.pc;
-    g.cl = g.cd + (size_t)g.CB * g.pc;
+    g.CB = min(max_col, (line_doubles - used) / (3 * g.pc));
+    g.cb = lines + used;
   }
+  g.cd = g.cb + (size_t)g.CB * g.pc;
+  g.cl = g.cd + (size_t)g.CB * g.pc;
 
   WideTeam tm;
   tm.ctr = reinterpret_cast<unsigned*>(L.counter) + 16 + 8 * team;
@@ -582,6 +599,12 @@ __global__ void __launch_bounds__(kWideThreads, 1) hadi_wide_kernel(const HadiLa
       hadi_phase_factor(it, w, vg, tid, kWideThreads, kWideThreads - 1);
       __syncthreads();
       w.Y = y_keep;
+      // A2 factor records of the column chains (the assembly scratch above is dead now; the records sit at the arena's start)
+      for (int j = tid; j <= m2; j += kWideThreads) {
+        double* rec = g.t2 + 6 * (kPad + j);
+        rec[0] = w.tj[TJ_F * w.n2 + j]; rec[1] = w.tj[TJ_G * w.n2 + j]; rec[2] = w.tj[TJ_MM * w.n2 + j];
+        rec[4] = w.tj[TJ_CP * w.n2 + j]; rec[5] = w.tj[TJ_C2P * w.n2 + j];
+      }
     }
     for (int p = gtid; p < (m2 + 1) * (m1 + 1); p += gnt) {
       const int j = p / (m1 + 1), i = p - j * (m1 + 1);
@@ -653,8 +676,8 @@ int hadi_wide_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj, H
   if (e != cudaSuccess) return (int)e;
   if (m2 + 1 > kWideThreads - 1 || m1 + 1 > 4096) return -1;
   const size_t tables = wide_table_bytes(n1, n2);
-  const size_t pr = (size_t)n1 + 2 * kCh, pc = ((size_t)n2 + 2 * kCh) | 1;
-  const size_t need = tables + sizeof(double) * std::max((size_t)TS_COUNT * n2, 6 * pr + 3 * pc);
+  const size_t pr = (size_t)n1 + 2 * kPad, pc = ((size_t)n2 + 2 * kPad) | 1;
+  const size_t need = tables + sizeof(double) * std::max((size_t)TS_COUNT * n2, 6 * ((size_t)n2 + 2 * kPad) + 6 * pr + 3 * pc);
   if (need + 1024 > (size_t)max_smem) return -1;
   const size_t smem = ((size_t)max_smem - 1024) & ~size_t(127);   // take the SM: one CTA per SM, the arena as large as it gets
   e = cudaFuncSetAttribute((const void*)hadi_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
