@@ -381,16 +381,22 @@ def c5_cpu_baseline():
 
 def config4_block(hadi, ctx, peaks, with_cpu):
     """BASELINE configs[3]: European Craig-Sneyd on the 401x201 grid, N = 200 — beyond shared memory, so U, Y and
-    the Craig-Sneyd stage arrays live in L2-resident global scratch (one CTA per solve; a thread-block cluster per
-    solve when there are few).  Memory-bound by construction: roofline = algorithmic bytes (9 arrays x 8 B x P per
-    step) over the kernel time, against the measured HBM copy bandwidth."""
+    the Craig-Sneyd stage arrays live in global scratch.  Batches of up to 48 such solves run on the wide kernel (one
+    solve on a team of co-resident CTAs, line solves out of shared memory), larger ones one CTA per solve.  Two bounds
+    are reported: the HBM roofline of SURVEY 8(d) (algorithmic bytes = 9 arrays x 8 B x P per step over the kernel
+    time, against the measured copy bandwidth), which is what bounds MANY solves, and for the few-solve regime the
+    dependent-chain floor of the line solves (per step two A1 sweeps of m1 nodes x 7 dependent FP64 operations and two
+    A2 sweeps of m2+1 nodes x 7, at the measured dependent-issue interval of `dep_cycles` cycles), which no amount of
+    parallel hardware shortens while the sweeps stay sequential (bit parity with the reference's Thomas order)."""
     m1, m2, N = 400, 200, 200
     Pl = (m1 + 1) * (m2 + 1)
     mdl = hadi.make_model(**BASE)
     num = hadi.make_numerics(m1, m2, THETA, hadi.EUROPEAN, hadi.CALL, hadi.CRAIG_SNEYD, None)
     out = {"workload": "config4: European call, Craig-Sneyd, 401x201 grid, N=200, strikes 100+0.1k"}
     hbm = peaks.get("hbm_gbs") or 6552.3
-    for nopt in (1, 8, 148):
+    dep_cycles, sm_ghz = 8.1, 1.965   # tools/ubench_lat.cu on B200; SM clock under load
+    chain_floor_ms = N * 2 * (m1 * 7 + (m2 + 1) * 7) * dep_cycles / (sm_ghz * 1e6)
+    for nopt in (1, 8, 37, 148):
         pts, n = hadi.make_points([100.0 + 0.1 * k for k in range(nopt)], 1.0, N)
         bt = ctx.batch(mdl, num, pts, n)
         ts = []
@@ -400,11 +406,17 @@ def config4_block(hadi, ctx, peaks, with_cpu):
             ts.append(bt.elapsed_ms())
         ms = min(ts)
         byts = nopt * N * Pl * 8 * 9
-        out["n%d" % nopt] = {"solves": nopt, "ms": round(ms, 3), "ms_per_solve": round(ms / nopt, 3),
-                             "solves_per_s": round(nopt / (ms * 1e-3), 2),
-                             "roofline": {"bound": "hbm", "achieved": round(byts / ms / 1e6, 1), "peak": hbm,
-                                          "unit": "GB/s", "frac": round(byts / ms / 1e6 / hbm, 4)},
-                             "price0": repr(float(v[0]))}
+        variant, ctas, per_solve = bt.kernel_info
+        ent = {"solves": nopt, "ms": round(ms, 3), "ms_per_solve": round(ms / nopt, 3),
+               "solves_per_s": round(nopt / (ms * 1e-3), 2),
+               "kernel": {"variant": variant, "ctas": ctas, "ctas_per_solve": per_solve},
+               "roofline": {"bound": "hbm", "achieved": round(byts / ms / 1e6, 1), "peak": hbm,
+                            "unit": "GB/s", "frac": round(byts / ms / 1e6 / hbm, 4)},
+               "price0": repr(float(v[0]))}
+        if nopt == 1:
+            ent["latency_bound"] = {"bound": "dependent FP64 chain of the line solves", "floor_ms": round(chain_floor_ms, 3),
+                                    "frac": round(chain_floor_ms / ms, 4)}
+        out["n%d" % nopt] = ent
         bt.destroy()
     out["golden_price_K100"] = "8.8920027296371611"
     if with_cpu:

@@ -183,6 +183,11 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
                          const hadi_point* points, int mode, const double* eps5, int item_begin, int item_end,
                          hadi_batch** out);
 int hadi_batch_num_items(const hadi_batch* b);
+/* Which kernel the library planned for this batch (diagnostics, benchmarks): variant id (0 / 1
+ * grid-specialised, 2 / 3 run-time dimensions, 5 / 6 one CTA per solve with the working set in global scratch, 7 one
+ * thread-block cluster per solve, 9 the wide kernel: one solve on a team of co-resident CTAs), CTAs of the launch and
+ * CTAs that share one solve.  Any pointer may be NULL. */
+int hadi_batch_kernel_info(const hadi_batch* b, int* variant, int* grid_ctas, int* ctas_per_solve);
 /* values each item publishes: 1, or 3 in HADI_MODE_JACOBIAN_INTERP */
 int hadi_batch_values_per_item(const hadi_batch* b);
 /* Re-aim a prepared batch at new Heston parameters (kappa, eta, sigma, rho, V0 of `model`; S0, r_d, r_f must be those

@@ -660,7 +660,9 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
   // (0 disables); HADI_FORCE_VARIANT=9 takes it for any grid and batch size.
   {
     const char* wm = getenv("HADI_WIDE_MAX_ITEMS");
-    const int wide_max = wm ? atoi(wm) : HADI_WIDE_MAX_ITEMS_DEFAULT;
+    // measured on B200 (tools/time_wide.py): 401 x 201 Craig-Sneyd breaks even with the one-CTA kernel near 50 solves,
+    // 101 x 51 near 100 (the smaller the grid, the more of its lines fit one CTA's shared memory at once)
+    const int wide_max = wm ? atoi(wm) : (P > 16384 ? HADI_WIDE_MAX_ITEMS_DEFAULT : 2 * HADI_WIDE_MAX_ITEMS_DEFAULT);
     if (num->num_dividends == 0 && n_it_plan >= 1 &&
         (forced_wide || (!forced_variant && plan.global_state && n_it_plan <= wide_max))) {
       const auto wkey = std::make_tuple(num->m1, num->m2, num->scheme, 2, std::string("wide"));
@@ -974,6 +976,13 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
 int hadi_batch_num_items(const hadi_batch* b) { return b ? b->n_items : 0; }
 long long hadi_batch_exact_reruns(const hadi_batch* b) { return b ? b->reruns : 0; }
 int hadi_batch_values_per_item(const hadi_batch* b) { return b ? b->stride : 0; }
+int hadi_batch_kernel_info(const hadi_batch* b, int* variant, int* grid_ctas, int* ctas_per_solve) {
+  if (!b) return HADI_ERR_ARG;
+  if (variant) *variant = b->plan.variant;
+  if (grid_ctas) *grid_ctas = b->grid_ctas;
+  if (ctas_per_solve) *ctas_per_solve = std::max(1, b->plan.cluster);
+  return HADI_OK;
+}
 double* hadi_batch_values_dev(hadi_batch* b) { return b ? b->L.out_values : nullptr; }
 
 // Re-aim a prepared batch at new Heston parameters (kappa, eta, sigma, rho, V0) without rebuilding it: the LM loop

@@ -69,14 +69,14 @@ struct WideTeam {
 __device__ __forceinline__ void wide_sync(WideTeam& tm, int tid) {
   __syncthreads();
   if (tm.G > 1 && tid == 0) {
+    // release: the CTA's writes (ordered before this point by the barrier above) are visible at GPU scope before the
+    // arrival is; acquire: what the other CTAs wrote before arriving is visible to this CTA after the barrier below
     tm.epoch += (unsigned)tm.G;
-    __threadfence();
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(tm.ctr) : "memory");
     unsigned v;
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(tm.ctr) : "memory");
     } while ((int)(v - tm.epoch) < 0);
-    __threadfence();
   }
   __syncthreads();
 }
@@ -700,7 +700,10 @@ int hadi_wide_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj, H
 // CTAs per solve for a batch of n_items on sm_count SMs: everything the GPU has, but no more CTAs than lines
 int hadi_wide_team(int n_items, int sm_count, int m1, int m2) {
   const int lines = std::max(m1 + 1, m2 + 1);
-  return std::max(1, std::min(sm_count / std::max(1, n_items), lines));
+  int G = std::max(1, std::min(sm_count / std::max(1, n_items), lines));
+  if (const char* t = getenv("HADI_WIDE_TEAM"))   // development aid: cap the team size
+    if (atoi(t) > 0) G = std::min(G, atoi(t));
+  return G;
 }
 
 int hadi_launch_wide(const HadiLaunch& L_in, const HadiPlan& plan, int grid_ctas, void* stream) {

@@ -38,7 +38,7 @@ EXPORTS = [
     "hadi_dividend_adjusted_spot", "hadi_market_prices", "hadi_implied_vols", "hadi_write_calibration_csv",
     "hadi_batch_create_ex", "hadi_batch_values_per_item", "hadi_jacobian_assemble_ex", "hadi_jacobian_v0_weight",
     "hadi_jacobian_batch_ex", "hadi_calibrate_ex", "hadi_plan_schedule", "hadi_exact_reruns",
-    "hadi_batch_exact_reruns", "hadi_nccl_unique_id", "hadi_comm_init", "hadi_comm_finalize", "hadi_comm_world",
+    "hadi_batch_exact_reruns", "hadi_batch_kernel_info", "hadi_nccl_unique_id", "hadi_comm_init", "hadi_comm_finalize", "hadi_comm_world",
     "hadi_comm_rank", "hadi_price_batch_sharded", "hadi_jacobian_batch_sharded", "hadi_batch_update_model",
 ]
 
@@ -140,6 +140,7 @@ def lib():
                                         C.POINTER(Point), C.c_int, C.c_double, C.c_int, C.c_int,
                                         C.POINTER(C.c_void_p)]
         L.hadi_batch_num_items.argtypes = [C.c_void_p]
+        L.hadi_batch_kernel_info.argtypes = [C.c_void_p, _ip, _ip, _ip]
         L.hadi_batch_launch.argtypes = [C.c_void_p]
         L.hadi_batch_values_dev.argtypes = [C.c_void_p]
         L.hadi_batch_values_dev.restype = C.c_void_p
@@ -573,6 +574,13 @@ class Batch:
     @property
     def exact_reruns(self):
         return lib().hadi_batch_exact_reruns(self._h)
+
+    @property
+    def kernel_info(self):
+        """(variant id, CTAs of the launch, CTAs per solve) the library planned for this batch."""
+        v, g, c = C.c_int(0), C.c_int(0), C.c_int(0)
+        self.ctx._check(lib().hadi_batch_kernel_info(self._h, C.byref(v), C.byref(g), C.byref(c)))
+        return v.value, g.value, c.value
 
     def elapsed_ms(self):
         ms = C.c_float(0.0)

@@ -418,6 +418,14 @@ def test_config4_full_size_golden(hadi, ctx):
     own code (SURVEY.md 8(c) probe): Craig-Sneyd host solver and device Douglas path."""
     g = solve_gpu_cs(hadi, ctx, [100.0] * 4, 200, 1.0, 400, 200)
     assert np.all(g["prices"] == 8.8920027296371611)
+    # which kernels the planner picks at this size: the wide kernel for a few solves, one CTA per solve for many
+    mdl = hadi.make_model(**BASE)
+    num = hadi.make_numerics(400, 200, 0.8, hadi.EUROPEAN, hadi.CALL, hadi.CRAIG_SNEYD, None)
+    for nopt, want in ((1, (9, 148, 148)), (4, (9, 148, 37)), (148, (5, 148, 1))):
+        pts, n = hadi.make_points([100.0] * nopt, 1.0, 200)
+        bt = ctx.batch(mdl, num, pts, n)
+        assert bt.kernel_info == want
+        bt.destroy()
     g = solve_gpu(hadi, ctx, [100.0], 200, 1.0, 400, 200)
     assert g["prices"][0] == 8.8925021574843157
 
