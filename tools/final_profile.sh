@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-end evidence on one B200 (run through gpurun from the repo root):
 #   tests, smoke, bench (own arm + reference arm), ncu launch list of the bench, one full ncu capture of a config-2
-#   launch and one of the large-grid kernels (variants 5 and 7).
+#   launch and one of each large-grid kernel (variants 5, 7 and 9).
 # Outputs land in gpurun_out/ with the tag given as $1; tools/ncu_summary.py turns them into profiles/*.txt.
 set -u
 TAG=${1:-r2}
@@ -18,4 +18,6 @@ HADI_FORCE_VARIANT=5 ncu --set full --clock-control none --import-source on -k r
     python tools/prof_large.py 148 20 > $OUT/prof_v5_$TAG.log 2>&1; echo "ncu variant 5 rc=$?"
 HADI_FORCE_VARIANT=7 ncu --set full --clock-control none --import-source on -k regex:hadi_cluster_kernel -s 1 -c 1 -f -o $OUT/prof_v7_$TAG \
     python tools/prof_large.py 1 20 > $OUT/prof_v7_$TAG.log 2>&1; echo "ncu variant 7 rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:hadi_wide_kernel -s 1 -c 1 -f -o $OUT/prof_v9_$TAG \
+    python tools/prof_large.py 1 20 > $OUT/prof_v9_$TAG.log 2>&1; echo "ncu variant 9 (wide kernel, one solve) rc=$?"
 ls -la $OUT/prof_*$TAG.ncu-rep
