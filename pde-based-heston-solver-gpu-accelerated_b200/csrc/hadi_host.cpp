@@ -22,6 +22,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <new>
 #include <vector>
 
 #include "../../include/hadi.h"
@@ -363,11 +364,17 @@ void v0_bracket(const double* v, int m2, double v0_pert, int* lo, int* hi, doubl
 
 }  // namespace
 
+// "nothing throws across the ABI" (include/hadi.h): the entry points that size std::vector / std::map from caller input are
+// function-try-blocks
+#define HADI_CATCH \
+  catch (const std::bad_alloc&) { return HADI_ERR_NOMEM; } \
+  catch (...) { return HADI_ERR_ARG; }
+
 extern "C" {
 
 const char* hadi_version(void) { return "hadi 0.1 (sm_100a)"; }
 
-int hadi_create(hadi_ctx** out, int device) {
+int hadi_create(hadi_ctx** out, int device) try {
   if (!out) return HADI_ERR_ARG;
   *out = nullptr;
   int count = 0;
@@ -388,7 +395,7 @@ int hadi_create(hadi_ctx** out, int device) {
   }
   *out = ctx;
   return HADI_OK;
-}
+} HADI_CATCH
 
 void hadi_destroy(hadi_ctx* ctx) {
   if (!ctx) return;
@@ -409,7 +416,7 @@ void hadi_destroy(hadi_ctx* ctx) {
 }
 
 // ---- in-library multi-GPU exchange -------------------------------------------------
-int hadi_nccl_unique_id(void* id128) {
+int hadi_nccl_unique_id(void* id128) try {
   if (!id128) return HADI_ERR_ARG;
   if (!nccl_api().ok()) return HADI_ERR_COMM;
   ncclUniqueId id;
@@ -417,9 +424,9 @@ int hadi_nccl_unique_id(void* id128) {
   static_assert(sizeof(id) == HADI_NCCL_ID_BYTES, "ncclUniqueId is 128 bytes");
   std::memcpy(id128, &id, sizeof id);
   return HADI_OK;
-}
+} HADI_CATCH
 
-int hadi_comm_init(hadi_ctx* ctx, int world, int rank, const void* id128) {
+int hadi_comm_init(hadi_ctx* ctx, int world, int rank, const void* id128) try {
   if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) return HADI_ERR_ARG;
   if (ctx->nccl) return fail(ctx, HADI_ERR_ARG, "a communicator is already attached");
   if (!nccl_api().ok()) return fail(ctx, HADI_ERR_COMM, "libnccl.so.2 could not be loaded (set HADI_NCCL_LIB)");
@@ -434,7 +441,7 @@ int hadi_comm_init(hadi_ctx* ctx, int world, int rank, const void* id128) {
   ctx->nccl_world = world;
   ctx->nccl_rank = rank;
   return HADI_OK;
-}
+} HADI_CATCH
 
 void hadi_comm_finalize(hadi_ctx* ctx) {
   if (!ctx || !ctx->nccl) return;
@@ -452,20 +459,20 @@ int hadi_comm_rank(const hadi_ctx* ctx) { return ctx ? ctx->nccl_rank : -1; }
 const char* hadi_last_error(const hadi_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
 long long hadi_kernel_launches(const hadi_ctx* ctx) { return ctx ? ctx->launches : 0; }
 long long hadi_exact_reruns(const hadi_ctx* ctx) { return ctx ? ctx->exact_reruns : 0; }
-int hadi_transfer_bytes(const hadi_ctx* ctx, long long* h2d, long long* d2h) {
+int hadi_transfer_bytes(const hadi_ctx* ctx, long long* h2d, long long* d2h) try {
   if (!ctx) return HADI_ERR_ARG;
   if (h2d) *h2d = ctx->h2d_bytes;
   if (d2h) *d2h = ctx->d2h_bytes;
   return HADI_OK;
-}
+} HADI_CATCH
 
-int hadi_grid(int m1, int m2, double K, double S0, double V0, double* s, double* v) {
+int hadi_grid(int m1, int m2, double K, double S0, double V0, double* s, double* v) try {
   if (m1 < 1 || m2 < 1 || !s || !v) return HADI_ERR_ARG;
   auto g = s_grid(nullptr, m1, K, S0);
   std::copy(g->begin(), g->end(), s);
   v_grid(nullptr, m2, V0, v);
   return HADI_OK;
-}
+} HADI_CATCH
 
 double hadi_bs_call(double S, double K, double r, double vol, double T) {
   // src/bs.hpp:44-55
@@ -477,16 +484,16 @@ double hadi_bs_call(double S, double K, double r, double vol, double T) {
   return S * std::erfc(-d1 / std::sqrt(2.0)) / 2.0 - K * std::exp(-r * T) * std::erfc(-d2 / std::sqrt(2.0)) / 2.0;
 }
 
-int hadi_item_costs(const hadi_numerics* num, int n, const hadi_point* points, int mode, int* costs) {
+int hadi_item_costs(const hadi_numerics* num, int n, const hadi_point* points, int mode, int* costs) try {
   if (!valid_numerics(num) || n < 0 || (n > 0 && (!points || !costs))) return HADI_ERR_ARG;
   const int nc = n_columns(mode);
   const int P = (num->m1 + 1) * (num->m2 + 1);
   for (int k = 0; k < n; ++k)
     for (int c = 0; c < nc; ++c) costs[k * nc + c] = points[k].time_steps * P;
   return HADI_OK;
-}
+} HADI_CATCH
 
-int hadi_partition(int n_items, const int* costs, int world, int rank, int* begin, int* end) {
+int hadi_partition(int n_items, const int* costs, int world, int rank, int* begin, int* end) try {
   if (n_items < 0 || world <= 0 || rank < 0 || rank >= world || !begin || !end) return HADI_ERR_ARG;
   // contiguous blocks; boundary r is the first item whose cost prefix reaches r/world of the total
   long long total = 0;
@@ -506,12 +513,12 @@ int hadi_partition(int n_items, const int* costs, int world, int rank, int* begi
   *begin = boundary(rank);
   *end = boundary(rank + 1);
   return HADI_OK;
-}
+} HADI_CATCH
 
 // Inspection / test aid: the split schedule hadi_batch_create builds for n solves of time_steps[k] steps
 // (in the order given) on `slots` persistent CTAs.
 int hadi_plan_schedule(int n, const int* time_steps, int slots, double setup, int max_segments, int* seg5,
-                       int* slot_off, double* heaviest_steps) {
+                       int* slot_off, double* heaviest_steps) try {
   if (n < 0 || (n > 0 && !time_steps) || slots < 1 || !seg5 || !slot_off) return HADI_ERR_ARG;
   std::vector<HadiItem> items((size_t)n);
   for (int k = 0; k < n; ++k) {
@@ -537,9 +544,9 @@ int hadi_plan_schedule(int n, const int* time_steps, int slots, double setup, in
     *heaviest_steps = hv;
   }
   return (int)sc.segs.size();
-}
+} HADI_CATCH
 
-int hadi_jacobian_assemble(int n, const double* v, double eps, double* J, double* base) {
+int hadi_jacobian_assemble(int n, const double* v, double eps, double* J, double* base) try {
   if (n < 0 || !v || !J || !base) return HADI_ERR_ARG;
   for (int k = 0; k < n; ++k) {
     const double b = v[6 * k];
@@ -547,19 +554,19 @@ int hadi_jacobian_assemble(int n, const double* v, double eps, double* J, double
     for (int c = 0; c < 5; ++c) J[5 * k + c] = (v[6 * k + 1 + c] - b) / eps;
   }
   return HADI_OK;
-}
+} HADI_CATCH
 
-int hadi_jacobian_v0_weight(int m2, double V0, double eps_v0, int* lower, int* upper, double* weight) {
+int hadi_jacobian_v0_weight(int m2, double V0, double eps_v0, int* lower, int* upper, double* weight) try {
   if (m2 < 1 || !lower || !upper || !weight) return HADI_ERR_ARG;
   std::vector<double> v((size_t)m2 + 1);
   v_grid(nullptr, m2, V0, v.data());
   v0_bracket(v.data(), m2, V0 + eps_v0, lower, upper, weight);
   return HADI_OK;
-}
+} HADI_CATCH
 
 // Jacobian rows from the item values of any Jacobian mode (layouts: include/hadi.h).
 int hadi_jacobian_assemble_ex(int n, int mode, const double* v, const double* eps5, double v0_weight, double* J,
-                              double* base) {
+                              double* base) try {
   if (n < 0 || !v || !eps5 || !J || !base) return HADI_ERR_ARG;
   if (mode == HADI_MODE_JACOBIAN) {
     // src/jacobian_computation.cpp:330,361
@@ -589,7 +596,7 @@ int hadi_jacobian_assemble_ex(int n, int mode, const double* v, const double* ep
     return HADI_ERR_ARG;
   }
   return HADI_OK;
-}
+} HADI_CATCH
 
 // ------------------------------------------------------------------------------------------------
 int hadi_batch_create(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
@@ -601,7 +608,7 @@ int hadi_batch_create(hadi_ctx* ctx, const hadi_model* model, const hadi_numeric
 
 int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
                          const hadi_point* points, int mode, const double* eps5, int item_begin, int item_end,
-                         hadi_batch** out) {
+                         hadi_batch** out) try {
   if (!ctx || !out) return HADI_ERR_ARG;
   *out = nullptr;
   if (!model || !valid_numerics(num) || n < 0 || (n > 0 && !points) || !eps5) return fail(ctx, HADI_ERR_ARG, "bad argument");
@@ -971,25 +978,25 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
   }
   *out = b.release();
   return HADI_OK;
-}
+} HADI_CATCH
 
 int hadi_batch_num_items(const hadi_batch* b) { return b ? b->n_items : 0; }
 long long hadi_batch_exact_reruns(const hadi_batch* b) { return b ? b->reruns : 0; }
 int hadi_batch_values_per_item(const hadi_batch* b) { return b ? b->stride : 0; }
-int hadi_batch_kernel_info(const hadi_batch* b, int* variant, int* grid_ctas, int* ctas_per_solve) {
+int hadi_batch_kernel_info(const hadi_batch* b, int* variant, int* grid_ctas, int* ctas_per_solve) try {
   if (!b) return HADI_ERR_ARG;
   if (variant) *variant = b->plan.variant;
   if (grid_ctas) *grid_ctas = b->grid_ctas;
   if (ctas_per_solve) *ctas_per_solve = std::max(1, b->plan.cluster);
   return HADI_OK;
-}
+} HADI_CATCH
 double* hadi_batch_values_dev(hadi_batch* b) { return b ? b->L.out_values : nullptr; }
 
 // Re-aim a prepared batch at new Heston parameters (kappa, eta, sigma, rho, V0) without rebuilding it: the LM loop
 // solves the same options dozens of times, and strikes, step tables, schedule and buffers do not depend on the
 // parameters.  Rewrites the parameter fields of the item descriptors and the (up to three) v-grids and uploads those
 // two ranges; S0, r_d, r_f must be the ones the batch was created with.  The previous launch must have been fetched.
-int hadi_batch_update_model(hadi_batch* b, const hadi_model* model) {
+int hadi_batch_update_model(hadi_batch* b, const hadi_model* model) try {
   if (!b || !model) return HADI_ERR_ARG;
   hadi_ctx* ctx = b->ctx;
   if (bits(model->S0) != bits(b->model0.S0) || bits(model->r_d) != bits(b->model0.r_d) || bits(model->r_f) != bits(b->model0.r_f))
@@ -1036,9 +1043,9 @@ int hadi_batch_update_model(hadi_batch* b, const hadi_model* model) {
   if (e != cudaSuccess) return cuda_fail(ctx, e, "H2D (model update)");
   ctx->h2d_bytes += (long long)(bytes_items + bytes_v);
   return HADI_OK;
-}
+} HADI_CATCH
 
-int hadi_batch_launch(hadi_batch* b) {
+int hadi_batch_launch(hadi_batch* b) try {
   if (!b) return HADI_ERR_ARG;
   hadi_ctx* ctx = b->ctx;
   cudaSetDevice(ctx->device);
@@ -1059,9 +1066,9 @@ int hadi_batch_launch(hadi_batch* b) {
   cudaEventRecord(b->ev1, ctx->stream);
   b->launched = true;
   return HADI_OK;
-}
+} HADI_CATCH
 
-int hadi_batch_fetch(hadi_batch* b, double* values) {
+int hadi_batch_fetch(hadi_batch* b, double* values) try {
   if (!b || (!values && b->n_items > 0)) return HADI_ERR_ARG;
   hadi_ctx* ctx = b->ctx;
   cudaSetDevice(ctx->device);
@@ -1079,9 +1086,9 @@ int hadi_batch_fetch(hadi_batch* b, double* values) {
   b->reruns = (long long)rr;
   ctx->exact_reruns += (long long)rr;
   return HADI_OK;
-}
+} HADI_CATCH
 
-int hadi_batch_elapsed_ms(hadi_batch* b, float* ms) {
+int hadi_batch_elapsed_ms(hadi_batch* b, float* ms) try {
   if (!b || !ms || !b->launched) return HADI_ERR_ARG;
   cudaSetDevice(b->ctx->device);
   cudaError_t e = cudaEventSynchronize(b->ev1);
@@ -1089,12 +1096,12 @@ int hadi_batch_elapsed_ms(hadi_batch* b, float* ms) {
   e = cudaEventElapsedTime(ms, b->ev0, b->ev1);
   if (e != cudaSuccess) return cuda_fail(b->ctx, e, "event elapsed");
   return HADI_OK;
-}
+} HADI_CATCH
 
 // Phase cycle counters of the last launch summed over CTAs (all zero unless the library was built
 // with -DHADI_PHASE_TIMING): [0] set-up, [1] dividend jump, [2] explicit stage, [3] A1 solves,
 // [4] A2 solves, [5] projection, [6] output, [7] item fetch.  Development aid.
-int hadi_batch_phase_cycles(hadi_batch* b, long long* out8) {
+int hadi_batch_phase_cycles(hadi_batch* b, long long* out8) try {
   if (!b || !out8 || !b->L.prof) return HADI_ERR_ARG;
   cudaSetDevice(b->ctx->device);
   cudaStreamSynchronize(b->ctx->stream);
@@ -1105,10 +1112,10 @@ int hadi_batch_phase_cycles(hadi_batch* b, long long* out8) {
   for (int c = 0; c < b->grid_ctas; ++c)
     for (int k = 0; k < 8; ++k) out8[k] += h[(size_t)c * 8 + k];
   return HADI_OK;
-}
+} HADI_CATCH
 
 // development aid (not part of include/hadi.h): raw per-CTA debug records, 8 long long per CTA
-int hadi_batch_prof_raw(hadi_batch* b, long long* out, int max_ctas) {
+int hadi_batch_prof_raw(hadi_batch* b, long long* out, int max_ctas) try {
   if (!b || !out || !b->L.prof) return HADI_ERR_ARG;
   cudaSetDevice(b->ctx->device);
   cudaStreamSynchronize(b->ctx->stream);
@@ -1116,7 +1123,7 @@ int hadi_batch_prof_raw(hadi_batch* b, long long* out, int max_ctas) {
   if (cudaMemcpy(out, b->L.prof, sizeof(long long) * 8 * (size_t)n, cudaMemcpyDeviceToHost) != cudaSuccess)
     return cuda_fail(b->ctx, cudaGetLastError(), "D2H prof");
   return n;
-}
+} HADI_CATCH
 
 void hadi_batch_destroy(hadi_batch* b) {
   if (!b) return;
@@ -1179,7 +1186,7 @@ static int run_items(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics
 }
 
 int hadi_price_batch(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
-                     const hadi_point* points, double* prices, double* U_out, double* lambda_out) {
+                     const hadi_point* points, double* prices, double* U_out, double* lambda_out) try {
   if (!ctx || !prices) return HADI_ERR_ARG;
   if (n < 0 || (n > 0 && !points)) return fail(ctx, HADI_ERR_ARG, "bad argument");
   std::vector<double> vals((size_t)std::max(n, 1));
@@ -1192,15 +1199,15 @@ int hadi_price_batch(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics
     prices[gi] = vals[k];
   }
   return HADI_OK;
-}
+} HADI_CATCH
 
 int hadi_jacobian_batch(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
-                        const hadi_point* points, double eps, double* J, double* base_prices) {
+                        const hadi_point* points, double eps, double* J, double* base_prices) try {
   hadi_jacobian_options jo;
   jo.mode = HADI_MODE_JACOBIAN;
   for (int c = 0; c < 5; ++c) jo.eps[c] = eps;
   return hadi_jacobian_batch_ex(ctx, model, num, n, points, &jo, J, base_prices);
-}
+} HADI_CATCH
 
 static bool valid_jopt(const hadi_jacobian_options* jo) {
   if (!jo) return false;
@@ -1213,7 +1220,7 @@ static bool valid_jopt(const hadi_jacobian_options* jo) {
 
 int hadi_jacobian_batch_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
                            const hadi_point* points, const hadi_jacobian_options* jo, double* J,
-                           double* base_prices) {
+                           double* base_prices) try {
   if (!ctx || !J || !base_prices) return HADI_ERR_ARG;
   if (!model || n < 0 || (n > 0 && !points) || !valid_numerics(num) || !valid_jopt(jo)) return fail(ctx, HADI_ERR_ARG, "bad argument");
   const size_t per_option = (size_t)n_columns(jo->mode) * values_per_item(jo->mode);
@@ -1231,7 +1238,7 @@ int hadi_jacobian_batch_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nu
     for (int c = 0; c < 5; ++c) J[5 * gi + c] = Jt[5 * k + c];
   }
   return HADI_OK;
-}
+} HADI_CATCH
 
 // One-call entry points over the attached communicator: every rank passes the same arguments, solves its
 // cost-balanced slice of the work items and receives every result (SPMD).
@@ -1240,7 +1247,7 @@ static int solve_all(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics
                      float* ms);
 
 int hadi_price_batch_sharded(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
-                             const hadi_point* points, double* prices) {
+                             const hadi_point* points, double* prices) try {
   if (!ctx || !prices) return HADI_ERR_ARG;
   if (!model || n < 0 || (n > 0 && !points) || !valid_numerics(num)) return fail(ctx, HADI_ERR_ARG, "bad argument");
   std::vector<double> vals((size_t)std::max(n, 1));
@@ -1252,11 +1259,11 @@ int hadi_price_batch_sharded(hadi_ctx* ctx, const hadi_model* model, const hadi_
     prices[gi] = vals[k];
   }
   return HADI_OK;
-}
+} HADI_CATCH
 
 int hadi_jacobian_batch_sharded(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
                                 const hadi_point* points, const hadi_jacobian_options* jo, double* J,
-                                double* base_prices) {
+                                double* base_prices) try {
   if (!ctx || !J || !base_prices) return HADI_ERR_ARG;
   if (!model || n < 0 || (n > 0 && !points) || !valid_numerics(num) || !valid_jopt(jo)) return fail(ctx, HADI_ERR_ARG, "bad argument");
   const size_t per_option = (size_t)n_columns(jo->mode) * values_per_item(jo->mode);
@@ -1274,11 +1281,11 @@ int hadi_jacobian_batch_sharded(hadi_ctx* ctx, const hadi_model* model, const ha
     for (int c = 0; c < 5; ++c) J[5 * gi + c] = Jt[5 * k + c];
   }
   return HADI_OK;
-}
+} HADI_CATCH
 
 // ---- Levenberg-Marquardt ----------------------------------------------------------------------
 // src/jacobian_computation.cpp:20-104
-int hadi_solve5(const double* Ain, const double* bin, double* x) {
+int hadi_solve5(const double* Ain, const double* bin, double* x) try {
   if (!Ain || !bin || !x) return HADI_ERR_ARG;
   const int N = 5;
   double A[25], b[5];
@@ -1318,11 +1325,11 @@ int hadi_solve5(const double* Ain, const double* bin, double* x) {
   }
   for (int i = 0; i < N; ++i) x[i] = b[i];
   return HADI_OK;
-}
+} HADI_CATCH
 
 // src/jacobian_computation.cpp:107-195.  The 5x5 normal equations are formed on the host in the
 // oracle's (ascending-k) summation order: 30 dot products of length n are not GPU work.
-int hadi_lm_update(int n, const double* J, const double* r, double lambda, double* delta) {
+int hadi_lm_update(int n, const double* J, const double* r, double lambda, double* delta) try {
   if (n < 0 || !J || !r || !delta) return HADI_ERR_ARG;
   double A[25], g[5];
   for (int i = 0; i < 5; ++i)
@@ -1338,7 +1345,7 @@ int hadi_lm_update(int n, const double* J, const double* r, double lambda, doubl
     g[i] = acc;
   }
   return hadi_solve5(A, g, delta);
-}
+} HADI_CATCH
 
 // A prepared batch plus what the exchange step needs: this rank's slice of the work items, the per-rank counts, and
 // how the values come back — directly (one GPU), through the context's NCCL communicator (the kernel epilogue
@@ -1470,19 +1477,19 @@ static int solve_all(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics
 // same loop with one (N, dt)).
 int hadi_calibrate(hadi_ctx* ctx, const hadi_model* initial, const hadi_numerics* num, int n,
                    const hadi_point* points, const double* market, const hadi_lm_options* opt,
-                   const hadi_comm* comm, hadi_lm_result* res) {
+                   const hadi_comm* comm, hadi_lm_result* res) try {
   if (!opt) return HADI_ERR_ARG;
   hadi_jacobian_options jo;
   jo.mode = HADI_MODE_JACOBIAN;
   for (int c = 0; c < 5; ++c) jo.eps[c] = opt->eps;
   return hadi_calibrate_ex(ctx, initial, num, n, points, market, opt, &jo, comm, res);
-}
+} HADI_CATCH
 
 // The same loop with the Jacobian taken as `jo` says (opt->eps is ignored).
 // HADI_MODE_JACOBIAN reproduces the reference's trajectory; the other modes change the numbers.
 int hadi_calibrate_ex(hadi_ctx* ctx, const hadi_model* initial, const hadi_numerics* num, int n,
                       const hadi_point* points, const double* market, const hadi_lm_options* opt,
-                      const hadi_jacobian_options* jo, const hadi_comm* comm, hadi_lm_result* res) {
+                      const hadi_jacobian_options* jo, const hadi_comm* comm, hadi_lm_result* res) try {
   if (!ctx || !initial || !points || !market || !opt || !res || n <= 0) return HADI_ERR_ARG;
   if (!valid_numerics(num) || !valid_jopt(jo)) return fail(ctx, HADI_ERR_ARG, "bad argument");
   const int jcols = n_columns(jo->mode);
@@ -1574,6 +1581,6 @@ int hadi_calibrate_ex(hadi_ctx* ctx, const hadi_model* initial, const hadi_numer
   res->gpu_ms = gpu_ms;
   res->exact_reruns = ctx->exact_reruns - reruns0;
   return HADI_OK;
-}
+} HADI_CATCH
 
 }  // extern "C"
