@@ -662,7 +662,7 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
     if (prc > 0) return cuda_fail(ctx, (cudaError_t)prc, "kernel plan");
     ctx->plans[plan_key] = std::make_pair(0, plan);
   }
-  // A few solves that need the global working set (large grids, the Craig-Sneyd family) and have no dividend jump: the
+  // A few solves that need the global working set (large grids, the Craig-Sneyd family): the
   // wide kernel spreads each over a team of co-resident CTAs (hadi_wide.cu).  HADI_WIDE_MAX_ITEMS moves the threshold
   // (0 disables); HADI_FORCE_VARIANT=9 takes it for any grid and batch size.
   {
@@ -670,8 +670,7 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
     // measured on B200 (tools/time_wide.py): 401 x 201 Craig-Sneyd breaks even with the one-CTA kernel near 50 solves,
     // 101 x 51 near 100 (the smaller the grid, the more of its lines fit one CTA's shared memory at once)
     const int wide_max = wm ? atoi(wm) : (P > 16384 ? HADI_WIDE_MAX_ITEMS_DEFAULT : 2 * HADI_WIDE_MAX_ITEMS_DEFAULT);
-    if (num->num_dividends == 0 && n_it_plan >= 1 &&
-        (forced_wide || (!forced_variant && plan.global_state && n_it_plan <= wide_max))) {
+    if (n_it_plan >= 1 && (forced_wide || (!forced_variant && plan.global_state && n_it_plan <= wide_max))) {
       const auto wkey = std::make_tuple(num->m1, num->m2, num->scheme, 2, std::string("wide"));
       auto wh = ctx->plans.find(wkey);
       if (wh == ctx->plans.end()) {
@@ -685,8 +684,6 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
       } else if (forced_wide) {
         return fail(ctx, HADI_ERR_SMEM, "the wide kernel does not take this grid");
       }
-    } else if (forced_wide) {
-      return fail(ctx, HADI_ERR_ARG, "the wide kernel does not take dividend jumps");
     }
   }
 

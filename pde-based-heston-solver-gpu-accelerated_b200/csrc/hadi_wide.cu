@@ -21,7 +21,7 @@
 // factorisation ARE those functions); results are bit-identical to every other variant.  Guarded divisions use the
 // in-line IEEE fallback (hadi_div<false, true>), so there is no re-solve pass.
 //
-// Replaces, for batches of a few solves without dividend jumps, the thread-block-cluster kernel of round 1
+// Replaces, for batches of a few solves, the thread-block-cluster kernel of round 1
 // (hadi_cluster_kernel, 8 CTAs, every phase through L2): 401 x 201 x 200 Craig-Sneyd 68 ms -> see DESIGN.md section 7.
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -512,6 +512,44 @@ __device__ __forceinline__ void wide_cols(const HadiItem& it, const HadiView& w,
   }
 }
 
+// Dividend jump (hadi_phase_div1 / div2) on the owned rows: the jump interpolates along s within a row, so every CTA jumps
+// its rows through a shared-memory copy of the old row and writes U in place; the multiplier array is not touched.
+// The caller follows with a team barrier (the explicit stage reads the neighbouring rows).
+__device__ __forceinline__ void wide_dividend(const HadiView& w, const WideGeo& g, double amount, double pct, int tid) {
+  const int m1 = w.m1, nc = m1 + 1;
+  const double* s = hadi_ti(w, TI_S);
+  for (int i = tid; i <= m1; i += kWideThreads) {
+    int idx;
+    double wt;
+    hadi_dividend_index(s, m1, amount, pct, i, idx, wt);
+    w.divk[i] = idx;
+    hadi_ti(w, TI_DIVW)[i] = wt;
+  }
+  for (int b0 = 0; b0 < g.nrow; b0 += g.RB) {
+    const int nb = min(g.RB, g.nrow - b0);
+    for (int idx = tid; idx < nb * nc; idx += kWideThreads) {
+      const int r = idx / nc, i = idx - r * nc;
+      g.rA[r * g.pr + kPad + i].x = wld(w.U + (g.rank + g.G * (b0 + r)) * w.ld + i);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nb * nc; idx += kWideThreads) {
+      const int r = idx / nc, i = idx - r * nc;
+      const double2* row = g.rA + r * g.pr + kPad;
+      const int k = w.divk[i];
+      const double wt = hadi_ti(w, TI_DIVW)[i];
+      double val;
+      if (k > 0)
+        val = (1.0 - wt) * row[k - 1].x + wt * row[k].x;
+      else if (k == 0)
+        val = row[0].x;
+      else
+        val = 0.0;
+      w.U[(g.rank + g.G * (b0 + r)) * w.ld + i] = val;
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(kWideThreads, 1) hadi_wide_kernel(const HadiLaunch L, const int G) {
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x;
@@ -526,7 +564,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) hadi_wide_kernel(const HadiLa
   double* sp = smem;
   w.ti = sp; sp += (size_t)TI_COUNT * w.n1;
   w.tj = sp; sp += (size_t)TJ_COUNT * w.n2;
-  w.divk = nullptr;
+  w.divk = reinterpret_cast<int*>(sp); sp += w.n1 / 2;   // n1 ints (n1 is a multiple of four)
   double* arena = sp;
   const int arena_doubles = L.dbg_phase;   // set by hadi_launch_wide: doubles of shared memory behind the tables
   double* scratch = L.scratch + (size_t)team * L.scratch_stride;
@@ -616,7 +654,20 @@ __global__ void __launch_bounds__(kWideThreads, 1) hadi_wide_kernel(const HadiLa
     wide_tick(pf, 0, tid);
     wide_sync(tm, tid);
     wide_tick(pf, 1, tid);
+    int div_cur = 0;
     for (int n = 1; n <= it.N; ++n) {
+      if (it.nd > 0) {
+        // device schedule: one dividend per step at most; extension: every dividend dated inside the step, in order
+        for (;;) {
+          const int hit = it.div_all ? hadi_dividend_next(n, it.dt, it.nd, L.div_dates, div_cur)
+                                     : hadi_dividend_at(n, it.dt, it.nd, L.div_dates, div_cur);
+          if (hit < 0) break;   // uniform across the team
+          wide_dividend(w, g, L.div_amounts[hit], L.div_pcts[hit], tid);
+          wide_sync(tm, tid);
+          wide_tick(pf, 1, tid);
+          if (!it.div_all) break;
+        }
+      }
       const double e0 = eg[n - 1], e1 = eg[n];
       if (L.scheme >= 1) {
         wide_rows<1>(it, w, cs, g, e0, e1, L.scheme, tid, pf);
@@ -662,7 +713,9 @@ __global__ void __launch_bounds__(kWideThreads, 1) hadi_wide_kernel(const HadiLa
   }
 }
 
-size_t wide_table_bytes(int n1, int n2) { return sizeof(double) * ((size_t)TI_COUNT * n1 + (size_t)TJ_COUNT * n2); }
+size_t wide_table_bytes(int n1, int n2) {
+  return sizeof(double) * ((size_t)TI_COUNT * n1 + (size_t)TJ_COUNT * n2) + sizeof(int) * (size_t)n1;
+}
 
 }  // namespace
 

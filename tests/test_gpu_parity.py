@@ -385,6 +385,20 @@ def test_wide_kernel_is_bit_equal(hadi, ctx, oracle, monkeypatch, m1, m2):
     for k in (0, 4):
         assert g["prices"][k] == o["price"] and np.array_equal(g["U"][k], o["U"])
         assert np.array_equal(g["lambda"][k], o["lambda"])
+    # dividend jumps (each CTA jumps its own rows through shared memory), the device schedule and the every-dividend one
+    for style in (0, 1):
+        o = oracle.solve(97.0, 7, 0.81 / 7, m1=m1, m2=m2, theta=0.8, style=style, divs=DIVS, **BASE)
+        g = solve_gpu(hadi, ctx, [97.0, 103.0, 97.0], 7, 0.81, m1, m2, style=style, divs=DIVS)
+        for k in (0, 2):
+            assert g["prices"][k] == o["price"] and np.array_equal(g["U"][k], o["U"])
+            if style:
+                assert np.array_equal(g["lambda"][k], o["lambda"])
+    divs2 = ([0.2, 0.21, 0.6], [0.5, 0.3, 0.2], [0.0, 0.01, 0.02])
+    o = oracle.solve(100.0, 5, 0.2, m1=m1, m2=m2, theta=0.8, style=1, divs=divs2, div_all=1, **BASE)
+    numd = hadi.make_numerics(m1, m2, 0.8, hadi.AMERICAN, hadi.CALL, hadi.DOUGLAS, divs2, dividend_schedule=hadi.DIVIDENDS_ALL)
+    ptsd, nd_ = hadi.make_points([100.0], 1.0, 5)
+    g = ctx.price_batch(mdl, numd, ptsd, nd_, want_U=True, want_lambda=True)
+    assert g["prices"][0] == o["price"] and np.array_equal(g["U"][0], o["U"]) and np.array_equal(g["lambda"][0], o["lambda"])
     for scheme in (1, 2, 3):
         o = oracle.solve(104.0, N, 1.0 / 100, m1=m1, m2=m2, theta=0.8, scheme=scheme, want_lambda=False, **BASE)
         num = hadi.make_numerics(m1, m2, 0.8, hadi.EUROPEAN, hadi.CALL, scheme, None)
@@ -397,12 +411,15 @@ def test_wide_kernel_is_bit_equal(hadi, ctx, oracle, monkeypatch, m1, m2):
     pts, n = hadi.make_points([93.0], 1.0, N)
     g = ctx.price_batch(mdl, num, pts, n, want_U=True, want_lambda=True)
     assert g["prices"][0] == o["price"] and np.array_equal(g["U"][0], o["U"]) and np.array_equal(g["lambda"][0], o["lambda"])
-    # more items than teams, mixed step counts; against the default kernels
+    # more items than teams, mixed step counts and maturities (the teams walk the cost-sorted item list with a stride);
+    # against the default kernels
     strikes = [90.0 + 0.1 * k for k in range(200)]
-    a = solve_gpu(hadi, ctx, strikes, N, N / 100.0, m1, m2)["prices"]
+    steps = [2 + (k * 7) % 5 for k in range(200)]
+    mats = [0.01 * st for st in steps]
+    a = solve_gpu(hadi, ctx, strikes, steps, mats, m1, m2)["prices"]
     monkeypatch.delenv("HADI_FORCE_VARIANT")
     monkeypatch.setenv("HADI_WIDE_MAX_ITEMS", "0")
-    b = solve_gpu(hadi, ctx, strikes, N, N / 100.0, m1, m2)["prices"]
+    b = solve_gpu(hadi, ctx, strikes, steps, mats, m1, m2)["prices"]
     assert np.array_equal(a, b)
     # interpolated-V0 Jacobian publishes three values per item
     num = hadi.make_numerics(m1, m2, 0.8)
