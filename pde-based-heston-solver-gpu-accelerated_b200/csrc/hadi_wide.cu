@@ -389,8 +389,16 @@ __device__ __forceinline__ void wide_chain_a2(double* __restrict__ b, double* __
     }
   }
 }
-// line r of a batch runs on lane r / warps of warp r % warps: the first 16 lines sit on 16 different warps
-__device__ __forceinline__ int wide_line_of_thread(int tid) { return (tid & 31) * kWideWarps + (tid >> 5); }
+// Line r of a batch of nb lines runs on warp r % W, lane r / W, with W = min(nb, kChainWarps) warps: the lanes of a warp
+// sweep in lockstep for free, while every extra WARP on a scheduler costs the others issue slots and FP64-pipe cycles
+// (a chain node is ~22 instructions per 57-cycle chain step; an FP64 instruction takes the sub-partition's pipe for two
+// cycles whatever its active lanes) — measured: 13 lines on 13 warps sweep 1.6 times slower than on 8.
+constexpr int kChainWarps = 8;   // two per scheduler
+__device__ __forceinline__ int wide_line_of_thread(int tid, int nb) {
+  const int W = min(nb, kChainWarps);
+  const int warp = tid >> 5, lane = tid & 31;
+  return warp < W ? lane * W + warp : 0x7fffffff;
+}
 
 // ---- stages -------------------------------------------------------------------------------------------------------------
 // A1 factor streams of owned row (batch slot r, row j) into the row buffers
@@ -434,7 +442,7 @@ __device__ __forceinline__ void wide_rows(const HadiItem& it, const HadiView& w,
     __syncthreads();
     wide_tick(pf, 2, tid);
     {
-      const int r = wide_line_of_thread(tid);
+      const int r = wide_line_of_thread(tid, nb);
       if (r < nb)
         wide_chain_a1(g.rA + r * g.pr + kPad, g.rB + r * g.pr + kPad, g.rC + r * g.pr + kPad, m1);
     }
@@ -485,7 +493,7 @@ __device__ __forceinline__ void wide_cols(const HadiItem& it, const HadiView& w,
     __syncthreads();
     wide_tick(pf, 5, tid);
     {
-      const int cc = wide_line_of_thread(tid);
+      const int cc = wide_line_of_thread(tid, nb);
       if (cc < nb)
         wide_chain_a2(g.cb + cc * g.pc + kPad, g.cd + cc * g.pc + kPad, g.t2 + 6 * kPad, tj, n2, m2);
     }
@@ -588,7 +596,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) hadi_wide_kernel(const HadiLa
   const int t2_doubles = 6 * (w.n2 + 2 * kPad);
   double* lines = arena + t2_doubles;
   const int line_doubles = arena_doubles - t2_doubles;
-  g.pr = w.n1 + 2 * kPad;
+  g.pr = (w.n1 + 2 * kPad) | 1;   // odd pitches: the lanes of a chain warp (one line each) hit different banks
   g.pc = (w.n2 + 2 * kPad) | 1;
   const int max_row = (m2 + G) / G, max_col = (m1 + G) / G;
   g.RB = min(max_row, line_doubles / (6 * g.pr));
@@ -729,7 +737,7 @@ int hadi_wide_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj, H
   if (e != cudaSuccess) return (int)e;
   if (m2 + 1 > kWideThreads - 1 || m1 + 1 > 4096) return -1;
   const size_t tables = wide_table_bytes(n1, n2);
-  const size_t pr = (size_t)n1 + 2 * kPad, pc = ((size_t)n2 + 2 * kPad) | 1;
+  const size_t pr = ((size_t)n1 + 2 * kPad) | 1, pc = ((size_t)n2 + 2 * kPad) | 1;
   const size_t need = tables + sizeof(double) * std::max((size_t)TS_COUNT * n2, 6 * ((size_t)n2 + 2 * kPad) + 6 * pr + 3 * pc);
   if (need + 1024 > (size_t)max_smem) return -1;
   const size_t smem = ((size_t)max_smem - 1024) & ~size_t(127);   // take the SM: one CTA per SM, the arena as large as it gets

@@ -11,7 +11,10 @@ L.hadi_batch_prof_raw.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.c_int]
 ctx = hadi.Context(0)
 mdl = hadi.make_model(S0=100.0, V0=0.04, r_d=0.025, r_f=0.0, rho=-0.9, sigma=0.3, kappa=1.5, eta=0.04)
 names = ["setup", "barrier", "rhs1", "a1chain", "a2chain", "rhs2", "store", "factors"]
-for (n, N, m1, m2, scheme) in [(1, 50, 400, 200, 1), (1, 50, 400, 200, 0), (8, 50, 400, 200, 1), (1, 50, 100, 50, 0)]:
+cases = [(1, 50, 400, 200, 1), (1, 50, 400, 200, 0), (8, 50, 400, 200, 1), (1, 50, 100, 50, 0)]
+if len(sys.argv) > 1:   # n,N,m1,m2,scheme ...
+    cases = [tuple(int(x) for x in a.split(",")) for a in sys.argv[1:]]
+for (n, N, m1, m2, scheme) in cases:
     num = hadi.make_numerics(m1, m2, 0.8, 0, 0, scheme, None)
     pts, n = hadi.make_points([100.0 + k for k in range(n)], 1.0, N)
     bt = ctx.batch(mdl, num, pts, n)
