@@ -36,27 +36,86 @@ struct HadiCsView {
   double *Y0, *R0, *R1, *R2;   // [m2+1][ld]
 };
 
-// 9-point A0 product at node (j, i) of array X (halo rows / zero frame coefficients as in phase E)
-HADI_HD double hadi_cs_a0(const HadiView& w, const double* X, int i, int j) {
-  const int ld = w.ld, n2 = w.n2;
-  const double* p = X + j * ld + i;
+// ---- the explicit products from neighbour VALUES (the callers fetch them: several rows at once from global memory, so
+// that more than one memory round trip is in flight per thread; the wide kernel with ld.global.cg).  Halo rows / zero
+// frame coefficients as in phase E: no index clamping. -----------------------------------------------------------------
+struct HadiNb {
+  double mm, m0, mp, zm, z0, zp, pm, p0, pp, m2, p2;   // (j-1, i-1..i+1), (j, i-1..i+1), (j+1, i-1..i+1), (j-2, i), (j+2, i)
+};
+// 9-point A0 product, l outer, k inner: phase E, operation for operation
+HADI_HD double hadi_nb_a0(const HadiView& w, const HadiNb& n, int i, int j) {
   const double rs = hadi_ti(w, TI_RS)[i];
   const double bsm = hadi_ti(w, TI_BSM)[i], bs0 = hadi_ti(w, TI_BS0)[i], bsp = hadi_ti(w, TI_BSP)[i];
   const double* tj = w.tj;
-  const double vj = tj[TJ_V * n2 + j];
-  const double cij = rs * vj;
+  const int n2 = w.n2;
+  const double cij = rs * tj[TJ_V * n2 + j];
   const double csm = cij * bsm, cs0 = cij * bs0, csp = cij * bsp;
   const double bm = tj[TJ_BVM * n2 + j], b0 = tj[TJ_BV0 * n2 + j], bp = tj[TJ_BVP * n2 + j];
-  double r0 = (csm * bm) * p[-ld - 1];
-  r0 += (cs0 * bm) * p[-ld];
-  r0 += (csp * bm) * p[-ld + 1];
-  r0 += (csm * b0) * p[-1];
-  r0 += (cs0 * b0) * p[0];
-  r0 += (csp * b0) * p[1];
-  r0 += (csm * bp) * p[ld - 1];
-  r0 += (cs0 * bp) * p[ld];
-  r0 += (csp * bp) * p[ld + 1];
+  double r0 = (csm * bm) * n.mm;
+  r0 += (cs0 * bm) * n.m0;
+  r0 += (csp * bm) * n.mp;
+  r0 += (csm * b0) * n.zm;
+  r0 += (cs0 * b0) * n.z0;
+  r0 += (csp * b0) * n.zp;
+  r0 += (csm * bp) * n.pm;
+  r0 += (cs0 * bp) * n.p0;
+  r0 += (csp * bp) * n.pp;
   return r0;
+}
+// A1 coefficients of node (j, i)
+HADI_HD void hadi_nb_a1c(const HadiView& w, int i, int j, double& lo, double& ma, double& up) {
+  const double a = hadi_ti(w, TI_HS2)[i] * w.tj[TJ_V * w.n2 + j];
+  lo = a * hadi_ti(w, TI_DSM)[i] + hadi_ti(w, TI_BBM)[i];
+  ma = a * hadi_ti(w, TI_DS0)[i] + hadi_ti(w, TI_BB0)[i] - hadi_ti(w, TI_HRD)[i];
+  up = a * hadi_ti(w, TI_DSP)[i] + hadi_ti(w, TI_BBP)[i];
+}
+// A1 product in the host order of the Craig-Sneyd family: main, lower, upper
+HADI_HD double hadi_nb_a1_host(const HadiView& w, const HadiNb& n, int i, int j) {
+  double lo, ma, up;
+  hadi_nb_a1c(w, i, j, lo, ma, up);
+  double r1 = ma * n.z0;
+  if (i > 0) r1 += lo * n.zm;
+  if (i < w.m1) r1 += up * n.zp;
+  return r1;
+}
+// A2 product (padded diagonals)
+HADI_HD double hadi_nb_a2(const HadiView& w, const HadiNb& n, int j) {
+  const double* tj = w.tj;
+  const int n2 = w.n2;
+  double r2 = tj[TJ_L2 * n2 + j] * n.m2 + tj[TJ_L1 * n2 + j] * n.m0 + tj[TJ_D0 * n2 + j] * n.z0 + tj[TJ_U1 * n2 + j] * n.p0;
+  r2 += tj[TJ_U2 * n2 + j] * n.p2;
+  return r2;
+}
+// Window of X over rows jb-2 .. jb+UNR+1 of column i and rows jb-1 .. jb+UNR of columns i-1, i+1: everything UNR
+// consecutive nodes of a column need, requested before the first is used.  Rows past the lower halo are clamped (their
+// values are never used: the nodes they would feed do not exist).
+#define HADI_CS_UNR 4
+template <int UNR>
+struct HadiWin {
+  double c0[UNR + 4], cm[UNR + 2], cp[UNR + 2];
+};
+template <int UNR>
+HADI_HD void hadi_win_load(const double* X, int ld, int i, int jb, int m2, HadiWin<UNR>& W) {
+#pragma unroll
+  for (int r = 0; r < UNR + 4; ++r) {
+    const int jr = (jb - 2 + r < m2 + 2) ? jb - 2 + r : m2 + 2;
+    W.c0[r] = X[jr * ld + i];
+  }
+#pragma unroll
+  for (int r = 0; r < UNR + 2; ++r) {
+    const int jr = (jb - 1 + r < m2 + 1) ? jb - 1 + r : m2 + 1;
+    W.cm[r] = X[jr * ld + i - 1];
+    W.cp[r] = X[jr * ld + i + 1];
+  }
+}
+template <int UNR>
+HADI_HD HadiNb hadi_win_nb(const HadiWin<UNR>& W, int k) {
+  HadiNb n;
+  n.mm = W.cm[k]; n.m0 = W.c0[k + 1]; n.mp = W.cp[k];
+  n.zm = W.cm[k + 1]; n.z0 = W.c0[k + 2]; n.zp = W.cp[k + 1];
+  n.pm = W.cm[k + 2]; n.p0 = W.c0[k + 3]; n.pp = W.cp[k + 2];
+  n.m2 = W.c0[k]; n.p2 = W.c0[k + 4];
+  return n;
 }
 
 // host boundary vectors at node (j, i): b1 at index m1*(j+1) (= node (j, m1-j), quirk Q3), b2 on the
@@ -68,45 +127,43 @@ HADI_HD void hadi_cs_bounds(const HadiItem& it, const HadiView& w, int i, int j,
 }
 
 // Predictor, explicit part: R0, R1, R2, Y0 and the right-hand side of the first A1 solve (into Y).
+// The point-wise stages of the global-state kernels stream P-sized arrays through L2 / HBM with one thread per column
+// walking down the rows; each thread fetches what HADI_CS_UNR rows need before it computes the first, so that four
+// memory round trips overlap where one was in flight (ncu, 148 solves of 401 x 201: these stages were 45 % of the
+// kernel, all of it long-scoreboard stall).
 HADI_HD void hadi_cs_predict(const HadiItem& it, const HadiView& w, const HadiCsView& cs, double e0, double e1,
                              int tid, int nt, int scheme = HADI_SCHEME_CS) {
-  const int m1 = w.m1, m2 = w.m2, ld = w.ld, n2 = w.n2;
+  const int m1 = w.m1, m2 = w.m2, ld = w.ld;
   const HadiMap mp = hadi_map(m1, m2, tid, nt);
   if (!mp.active) return;
   const int i = mp.i;
   const double dt = it.dt, c = w.c;
-  const double hs2 = hadi_ti(w, TI_HS2)[i];
-  const double dsm = hadi_ti(w, TI_DSM)[i], ds0 = hadi_ti(w, TI_DS0)[i], dsp = hadi_ti(w, TI_DSP)[i];
-  const double bbm = hadi_ti(w, TI_BBM)[i], bb0 = hadi_ti(w, TI_BB0)[i], bbp = hadi_ti(w, TI_BBP)[i];
-  const double hrd = hadi_ti(w, TI_HRD)[i];
-  const double* tj = w.tj;
-  for (int j = mp.j0; j < mp.j1; ++j) {
-    const double* p = w.U + j * ld + i;
-    const double x = p[0];
-    const double r0 = hadi_cs_a0(w, w.U, i, j);
-    // A1, host order: main, lower, upper
-    const double a = hs2 * tj[TJ_V * n2 + j];
-    const double lo = a * dsm + bbm;
-    const double ma = a * ds0 + bb0 - hrd;
-    const double up = a * dsp + bbp;
-    double r1 = ma * x;
-    if (i > 0) r1 += lo * p[-1];
-    if (i < m1) r1 += up * p[1];
-    // A2 (padded diagonals, as phase E)
-    double r2 = tj[TJ_L2 * n2 + j] * p[-2 * ld] + tj[TJ_L1 * n2 + j] * p[-ld] + tj[TJ_D0 * n2 + j] * x +
-                tj[TJ_U1 * n2 + j] * p[ld];
-    r2 += tj[TJ_U2 * n2 + j] * p[2 * ld];
-    double b1p, b2p;
-    hadi_cs_bounds(it, w, i, j, b1p, b2p);
-    const double bb = 0.0 + b1p + b2p;
-    const double y0 = x + dt * (r0 + r1 + r2 + bb * e0);
-    const int q = j * ld + i;
-    cs.R0[q] = r0;
-    cs.R1[q] = r1;
-    cs.R2[q] = r2;
-    const double rhs = y0 + c * (b1p * e1 - (r1 + b1p * e0));
-    cs.Y0[q] = (scheme == HADI_SCHEME_MCS) ? rhs : y0;   // the shipped MCS keeps the overwritten Y_0 (src/solver.hpp:968)
-    w.Y[q] = rhs;
+  constexpr int UNR = HADI_CS_UNR;
+  for (int jb = mp.j0; jb < mp.j1; jb += UNR) {
+    HadiWin<UNR> W;
+    hadi_win_load<UNR>(w.U, ld, i, jb, m2, W);
+#pragma unroll
+    for (int k = 0; k < UNR; ++k) {
+      const int j = jb + k;
+      if (j < mp.j1) {
+        const HadiNb n = hadi_win_nb<UNR>(W, k);
+        const double x = n.z0;
+        const double r0 = hadi_nb_a0(w, n, i, j);
+        const double r1 = hadi_nb_a1_host(w, n, i, j);   // A1, host order: main, lower, upper
+        const double r2 = hadi_nb_a2(w, n, j);           // A2 (padded diagonals, as phase E)
+        double b1p, b2p;
+        hadi_cs_bounds(it, w, i, j, b1p, b2p);
+        const double bb = 0.0 + b1p + b2p;
+        const double y0 = x + dt * (r0 + r1 + r2 + bb * e0);
+        const int q = j * ld + i;
+        cs.R0[q] = r0;
+        cs.R1[q] = r1;
+        cs.R2[q] = r2;
+        const double rhs = y0 + c * (b1p * e1 - (r1 + b1p * e0));
+        cs.Y0[q] = (scheme == HADI_SCHEME_MCS) ? rhs : y0;   // the shipped MCS keeps the overwritten Y_0 (src/solver.hpp:968)
+        w.Y[q] = rhs;
+      }
+    }
   }
 }
 
@@ -118,11 +175,24 @@ HADI_HD void hadi_cs_rhs2(const HadiItem& it, const HadiView& w, const HadiCsVie
   if (!mp.active) return;
   const int i = mp.i;
   const double c = w.c;
-  for (int j = mp.j0; j < mp.j1; ++j) {
-    double b1p, b2p;
-    hadi_cs_bounds(it, w, i, j, b1p, b2p);
-    const int q = j * ld + i;
-    w.Y[q] = w.Y[q] + c * (b2p * e1 - (cs.R2[q] + b2p * e0));
+  constexpr int UNR = 2 * HADI_CS_UNR;
+  for (int jb = mp.j0; jb < mp.j1; jb += UNR) {
+    double yv[UNR], rv[UNR];
+#pragma unroll
+    for (int k = 0; k < UNR; ++k) {
+      const int j = (jb + k < mp.j1) ? jb + k : mp.j1 - 1;
+      yv[k] = w.Y[j * ld + i];
+      rv[k] = cs.R2[j * ld + i];
+    }
+#pragma unroll
+    for (int k = 0; k < UNR; ++k) {
+      const int j = jb + k;
+      if (j < mp.j1) {
+        double b1p, b2p;
+        hadi_cs_bounds(it, w, i, j, b1p, b2p);
+        w.Y[j * ld + i] = yv[k] + c * (b2p * e1 - (rv[k] + b2p * e0));
+      }
+    }
   }
 }
 
@@ -135,32 +205,31 @@ HADI_HD void hadi_cs_correct(const HadiItem& it, const HadiView& w, const HadiCs
   if (!mp.active) return;
   const int i = mp.i;
   const double dt = it.dt, c = w.c;
-  for (int j = mp.j0; j < mp.j1; ++j) {
-    const double a0y2 = hadi_cs_a0(w, w.U, i, j);
-    double b1p, b2p;
-    hadi_cs_bounds(it, w, i, j, b1p, b2p);
-    const int q = j * ld + i;
-    const double y0t = cs.Y0[q] + 0.5 * dt * ((a0y2 + 0.0 * e1) - (cs.R0[q] + 0.0 * e0));
-    w.Y[q] = y0t + c * (b1p * e1 - (cs.R1[q] + b1p * e0));
+  constexpr int UNR = HADI_CS_UNR;
+  for (int jb = mp.j0; jb < mp.j1; jb += UNR) {
+    HadiWin<UNR> W;
+    hadi_win_load<UNR>(w.U, ld, i, jb, m2, W);
+    double y0v[UNR], r0v[UNR], r1v[UNR];
+#pragma unroll
+    for (int k = 0; k < UNR; ++k) {
+      const int q = ((jb + k < mp.j1) ? jb + k : mp.j1 - 1) * ld + i;
+      y0v[k] = cs.Y0[q];
+      r0v[k] = cs.R0[q];
+      r1v[k] = cs.R1[q];
+    }
+#pragma unroll
+    for (int k = 0; k < UNR; ++k) {
+      const int j = jb + k;
+      if (j < mp.j1) {
+        const HadiNb n = hadi_win_nb<UNR>(W, k);
+        const double a0y2 = hadi_nb_a0(w, n, i, j);
+        double b1p, b2p;
+        hadi_cs_bounds(it, w, i, j, b1p, b2p);
+        const double y0t = y0v[k] + 0.5 * dt * ((a0y2 + 0.0 * e1) - (r0v[k] + 0.0 * e0));
+        w.Y[j * ld + i] = y0t + c * (b1p * e1 - (r1v[k] + b1p * e0));
+      }
+    }
   }
-}
-
-// A1 (host order: main, lower, upper) and A2 products at node (j, i) of array X — the predictor's expressions
-HADI_HD void hadi_cs_a1a2(const HadiItem& it, const HadiView& w, const double* X, int i, int j, double& r1, double& r2) {
-  const int m1 = w.m1, ld = w.ld, n2 = w.n2;
-  (void)it;
-  const double* tj = w.tj;
-  const double* p = X + j * ld + i;
-  const double x = p[0];
-  const double a = hadi_ti(w, TI_HS2)[i] * tj[TJ_V * n2 + j];
-  const double lo = a * hadi_ti(w, TI_DSM)[i] + hadi_ti(w, TI_BBM)[i];
-  const double ma = a * hadi_ti(w, TI_DS0)[i] + hadi_ti(w, TI_BB0)[i] - hadi_ti(w, TI_HRD)[i];
-  const double up = a * hadi_ti(w, TI_DSP)[i] + hadi_ti(w, TI_BBP)[i];
-  r1 = ma * x;
-  if (i > 0) r1 += lo * p[-1];
-  if (i < m1) r1 += up * p[1];
-  r2 = tj[TJ_L2 * n2 + j] * p[-2 * ld] + tj[TJ_L1 * n2 + j] * p[-ld] + tj[TJ_D0 * n2 + j] * x + tj[TJ_U1 * n2 + j] * p[ld];
-  r2 += tj[TJ_U2 * n2 + j] * p[2 * ld];
 }
 
 // Correctors of the Modified Craig-Sneyd (as shipped) and Hundsdorfer-Verwer schemes; Y2 sits in U.  Both need
@@ -174,25 +243,44 @@ HADI_HD void hadi_cs_correct2(const HadiItem& it, const HadiView& w, const HadiC
   if (!mp.active) return;
   const int i = mp.i;
   const double dt = it.dt, c = w.c, theta = it.theta;
-  for (int j = mp.j0; j < mp.j1; ++j) {
-    const double a0y2 = hadi_cs_a0(w, w.U, i, j);
-    double a1y2, a2y2;
-    hadi_cs_a1a2(it, w, w.U, i, j, a1y2, a2y2);
-    double b1p, b2p;
-    hadi_cs_bounds(it, w, i, j, b1p, b2p);
-    const double bb = 0.0 + b1p + b2p;
-    const int q = j * ld + i;
-    const double prev = cs.R0[q] + cs.R1[q] + cs.R2[q] + bb * e0;
-    const double curr = a0y2 + a1y2 + a2y2 + bb * e1;
-    if (scheme == HADI_SCHEME_MCS) {
-      const double f0n = a0y2 + 0.0 * e1, f0m = cs.R0[q] + 0.0 * e0;
-      const double y0h = cs.Y0[q] + c * (f0n - f0m);
-      const double y0t = y0h + (0.5 - theta) * dt * (curr - prev);
-      w.Y[q] = y0t + c * (b1p * e1 - (cs.R1[q] + b1p * e0));
-    } else {
-      const double y0t = cs.Y0[q] + 0.5 * dt * (curr - prev);
-      w.Y[q] = y0t + c * (b1p * e1 - (a1y2 + b1p * e1));
-      cs.R2[q] = a2y2;
+  constexpr int UNR = HADI_CS_UNR;
+  for (int jb = mp.j0; jb < mp.j1; jb += UNR) {
+    HadiWin<UNR> W;
+    hadi_win_load<UNR>(w.U, ld, i, jb, m2, W);
+    double y0v[UNR], r0v[UNR], r1v[UNR], r2v[UNR];
+#pragma unroll
+    for (int k = 0; k < UNR; ++k) {
+      const int q = ((jb + k < mp.j1) ? jb + k : mp.j1 - 1) * ld + i;
+      y0v[k] = cs.Y0[q];
+      r0v[k] = cs.R0[q];
+      r1v[k] = cs.R1[q];
+      r2v[k] = cs.R2[q];
+    }
+#pragma unroll
+    for (int k = 0; k < UNR; ++k) {
+      const int j = jb + k;
+      if (j < mp.j1) {
+        const HadiNb n = hadi_win_nb<UNR>(W, k);
+        const double a0y2 = hadi_nb_a0(w, n, i, j);
+        const double a1y2 = hadi_nb_a1_host(w, n, i, j);
+        const double a2y2 = hadi_nb_a2(w, n, j);
+        double b1p, b2p;
+        hadi_cs_bounds(it, w, i, j, b1p, b2p);
+        const double bb = 0.0 + b1p + b2p;
+        const int q = j * ld + i;
+        const double prev = r0v[k] + r1v[k] + r2v[k] + bb * e0;
+        const double curr = a0y2 + a1y2 + a2y2 + bb * e1;
+        if (scheme == HADI_SCHEME_MCS) {
+          const double f0n = a0y2 + 0.0 * e1, f0m = r0v[k] + 0.0 * e0;
+          const double y0h = y0v[k] + c * (f0n - f0m);
+          const double y0t = y0h + (0.5 - theta) * dt * (curr - prev);
+          w.Y[q] = y0t + c * (b1p * e1 - (r1v[k] + b1p * e0));
+        } else {
+          const double y0t = y0v[k] + 0.5 * dt * (curr - prev);
+          w.Y[q] = y0t + c * (b1p * e1 - (a1y2 + b1p * e1));
+          cs.R2[q] = a2y2;
+        }
+      }
     }
   }
 }

@@ -98,10 +98,8 @@ struct WideGeo {
   double* t2;        // [n2 + 2 kPad][6] A2 factor records {F, G, MM, -, CP, C2P}, row j at record kPad + j
 };
 
-// the 11 neighbours of node (j, i) the explicit operators need
-struct WideNb {
-  double mm, m0, mp, zm, z0, zp, pm, p0, pp, m2, p2;
-};
+// the 11 neighbours of node (j, i) the explicit operators need (products: hadi_nb_* in hadi_phases_cs.cuh)
+using WideNb = HadiNb;
 __device__ __forceinline__ WideNb wide_nb(const double* X, int ld, int i, int j) {
   const double* p = X + j * ld + i;
   WideNb n;
@@ -110,49 +108,6 @@ __device__ __forceinline__ WideNb wide_nb(const double* X, int ld, int i, int j)
   n.pm = wld(p + ld - 1); n.p0 = wld(p + ld); n.pp = wld(p + ld + 1);
   n.m2 = wld(p - 2 * ld); n.p2 = wld(p + 2 * ld);
   return n;
-}
-// A0 product, l outer, k inner (hadi_cs_a0 / phase E)
-__device__ __forceinline__ double wide_a0(const HadiView& w, const WideNb& n, int i, int j) {
-  const double rs = hadi_ti(w, TI_RS)[i];
-  const double bsm = hadi_ti(w, TI_BSM)[i], bs0 = hadi_ti(w, TI_BS0)[i], bsp = hadi_ti(w, TI_BSP)[i];
-  const double* tj = w.tj;
-  const int n2 = w.n2;
-  const double cij = rs * tj[TJ_V * n2 + j];
-  const double csm = cij * bsm, cs0 = cij * bs0, csp = cij * bsp;
-  const double bm = tj[TJ_BVM * n2 + j], b0 = tj[TJ_BV0 * n2 + j], bp = tj[TJ_BVP * n2 + j];
-  double r0 = (csm * bm) * n.mm;
-  r0 += (cs0 * bm) * n.m0;
-  r0 += (csp * bm) * n.mp;
-  r0 += (csm * b0) * n.zm;
-  r0 += (cs0 * b0) * n.z0;
-  r0 += (csp * b0) * n.zp;
-  r0 += (csm * bp) * n.pm;
-  r0 += (cs0 * bp) * n.p0;
-  r0 += (csp * bp) * n.pp;
-  return r0;
-}
-// A1 coefficients of node (j, i)
-__device__ __forceinline__ void wide_a1c(const HadiView& w, int i, int j, double& lo, double& ma, double& up) {
-  const double a = hadi_ti(w, TI_HS2)[i] * w.tj[TJ_V * w.n2 + j];
-  lo = a * hadi_ti(w, TI_DSM)[i] + hadi_ti(w, TI_BBM)[i];
-  ma = a * hadi_ti(w, TI_DS0)[i] + hadi_ti(w, TI_BB0)[i] - hadi_ti(w, TI_HRD)[i];
-  up = a * hadi_ti(w, TI_DSP)[i] + hadi_ti(w, TI_BBP)[i];
-}
-// A1 product in the host order of the Craig-Sneyd family: main, lower, upper (hadi_cs_predict)
-__device__ __forceinline__ double wide_a1_host(const HadiView& w, const WideNb& n, int i, int j) {
-  double lo, ma, up;
-  wide_a1c(w, i, j, lo, ma, up);
-  double r1 = ma * n.z0;
-  if (i > 0) r1 += lo * n.zm;
-  if (i < w.m1) r1 += up * n.zp;
-  return r1;
-}
-__device__ __forceinline__ double wide_a2(const HadiView& w, const WideNb& n, int j) {
-  const double* tj = w.tj;
-  const int n2 = w.n2;
-  double r2 = tj[TJ_L2 * n2 + j] * n.m2 + tj[TJ_L1 * n2 + j] * n.m0 + tj[TJ_D0 * n2 + j] * n.z0 + tj[TJ_U1 * n2 + j] * n.p0;
-  r2 += tj[TJ_U2 * n2 + j] * n.p2;
-  return r2;
 }
 
 // ---- right-hand sides of the A1 sweeps, one node ----------------------------------------------------------------------
@@ -164,11 +119,11 @@ __device__ __forceinline__ double wide_node_explicit(const HadiItem& it, const H
   const bool am = it.style == 1;
   const WideNb n = wide_nb(w.U, w.ld, i, j);
   const double x = n.z0;
-  const double r0 = wide_a0(w, n, i, j);
+  const double r0 = hadi_nb_a0(w, n, i, j);
   double lo, ma, upc;
-  wide_a1c(w, i, j, lo, ma, upc);
+  hadi_nb_a1c(w, i, j, lo, ma, upc);
   const double r1 = lo * n.zm + ma * x + upc * n.zp;
-  const double r2 = wide_a2(w, n, j);
+  const double r2 = hadi_nb_a2(w, n, j);
   const double lam_cur = am ? wld(w.lam + j * w.ld + i) : 0.0;
   const bool is_b1 = (i + j == m1);
   double y;
@@ -195,9 +150,9 @@ __device__ __forceinline__ double wide_node_predict(const HadiItem& it, const Ha
   const double dt = it.dt, c = w.c;
   const WideNb n = wide_nb(w.U, w.ld, i, j);
   const double x = n.z0;
-  const double r0 = wide_a0(w, n, i, j);
-  const double r1 = wide_a1_host(w, n, i, j);
-  const double r2 = wide_a2(w, n, j);
+  const double r0 = hadi_nb_a0(w, n, i, j);
+  const double r1 = hadi_nb_a1_host(w, n, i, j);
+  const double r2 = hadi_nb_a2(w, n, j);
   double b1p, b2p;
   hadi_cs_bounds(it, w, i, j, b1p, b2p);
   const double bb = 0.0 + b1p + b2p;
@@ -215,7 +170,7 @@ __device__ __forceinline__ double wide_node_correct(const HadiItem& it, const Ha
                                                     double e1, int i, int j, int scheme) {
   const double dt = it.dt, c = w.c, theta = it.theta;
   const WideNb n = wide_nb(w.U, w.ld, i, j);
-  const double a0y2 = wide_a0(w, n, i, j);
+  const double a0y2 = hadi_nb_a0(w, n, i, j);
   double b1p, b2p;
   hadi_cs_bounds(it, w, i, j, b1p, b2p);
   const int q = j * w.ld + i;
@@ -223,8 +178,8 @@ __device__ __forceinline__ double wide_node_correct(const HadiItem& it, const Ha
     const double y0t = wld(cs.Y0 + q) + 0.5 * dt * ((a0y2 + 0.0 * e1) - (wld(cs.R0 + q) + 0.0 * e0));
     return y0t + c * (b1p * e1 - (wld(cs.R1 + q) + b1p * e0));
   }
-  const double a1y2 = wide_a1_host(w, n, i, j);
-  const double a2y2 = wide_a2(w, n, j);
+  const double a1y2 = hadi_nb_a1_host(w, n, i, j);
+  const double a2y2 = hadi_nb_a2(w, n, j);
   const double bb = 0.0 + b1p + b2p;
   const double R0 = wld(cs.R0 + q), R1 = wld(cs.R1 + q), R2 = wld(cs.R2 + q);
   const double prev = R0 + R1 + R2 + bb * e0;
