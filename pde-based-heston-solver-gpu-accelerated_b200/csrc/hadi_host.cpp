@@ -667,8 +667,8 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
   // (0 disables); HADI_FORCE_VARIANT=9 takes it for any grid and batch size.
   {
     const char* wm = getenv("HADI_WIDE_MAX_ITEMS");
-    // measured on B200 (tools/time_wide.py): 401 x 201 Craig-Sneyd breaks even with the one-CTA kernel near 50 solves,
-    // 101 x 51 near 100 (the smaller the grid, the more of its lines fit one CTA's shared memory at once)
+    // measured on B200 (tools/time_wide.py): 401 x 201 Craig-Sneyd breaks even with the one-CTA kernel near 40 solves,
+    // 101 x 51 near 80 (the smaller the grid, the more of its lines fit one CTA's shared memory at once)
     const int wide_max = wm ? atoi(wm) : (P > 16384 ? HADI_WIDE_MAX_ITEMS_DEFAULT : 2 * HADI_WIDE_MAX_ITEMS_DEFAULT);
     if (n_it_plan >= 1 && (forced_wide || (!forced_variant && plan.global_state && n_it_plan <= wide_max))) {
       const auto wkey = std::make_tuple(num->m1, num->m2, num->scheme, 2, std::string("wide"));

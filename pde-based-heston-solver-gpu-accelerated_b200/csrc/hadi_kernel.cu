@@ -308,8 +308,10 @@ __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiI
     HADI_SYNC();
 #else
     if constexpr (M1 == 0) {
-      hadi_phase_rhs2<M1, M2>(it, w, e0, e1, tid, NT);
-      HADI_SYNC();
+      if (!w.gstate) {   // uniform: the global-state kernels fold phase R into the column solve below
+        hadi_phase_rhs2<M1, M2>(it, w, e0, e1, tid, NT);
+        HADI_SYNC();
+      }
     }
 #endif
     HADI_TICK(7)
@@ -321,7 +323,8 @@ __device__ __forceinline__ bool hadi_solve_item(const HadiLaunch& L, const HadiI
         if (n < it.N) hadi_fast_prestage<M1, M2>(w, tid, n);   // the feeder warps are idle in this phase
       }
     } else {
-      hadi_phase_solve_a2<M1, M2, EXACT>(it, w, tid, NT, bad);
+      // global-state kernels: phase R rides on the operand fetch of the forward sweep (one pass over Y and a barrier less)
+      hadi_phase_solve_a2<M1, M2, EXACT>(it, w, tid, NT, bad, HadiRhs2{w.gstate ? 1 : 0, nullptr, e0, e1});
     }
     if (it.bc && tid * w.line_mul + w.line_off == 0) hadi_dirichlet_col0(w, it.K * eg[it.N + 1 + n]);
     HADI_SYNC();
@@ -405,18 +408,15 @@ __device__ __forceinline__ bool hadi_solve_item_cs(const HadiLaunch& L, const Ha
     HADI_SYNC();
     hadi_phase_solve_a1<0, 0, EXACT>(it, w, e0, e1, 2 * n - 1, tid, NT, feed, bad, nullptr, 2 * it.N);
     HADI_SYNC();
-    hadi_cs_rhs2(it, w, cs, e0, e1, tid, NT);
-    HADI_SYNC();
-    hadi_phase_solve_a2<0, 0, EXACT>(it, w, tid, NT, bad);   // Y2 -> U
+    // hadi_cs_rhs2 rides on the operand fetch of the A2 forward sweep (HadiRhs2 mode 2)
+    hadi_phase_solve_a2<0, 0, EXACT>(it, w, tid, NT, bad, HadiRhs2{2, cs.R2, e0, e1});   // Y2 -> U
     HADI_SYNC();
     if (L.scheme == HADI_SCHEME_CS) hadi_cs_correct(it, w, cs, e0, e1, tid, NT);
     else hadi_cs_correct2(it, w, cs, e0, e1, tid, NT, L.scheme);
     HADI_SYNC();
     hadi_phase_solve_a1<0, 0, EXACT>(it, w, e0, e1, 2 * n, tid, NT, feed, bad, nullptr, 2 * it.N);
     HADI_SYNC();
-    hadi_cs_rhs2(it, w, cs, L.scheme == HADI_SCHEME_HV ? e1 : e0, e1, tid, NT);
-    HADI_SYNC();
-    hadi_phase_solve_a2<0, 0, EXACT>(it, w, tid, NT, bad);
+    hadi_phase_solve_a2<0, 0, EXACT>(it, w, tid, NT, bad, HadiRhs2{2, cs.R2, L.scheme == HADI_SCHEME_HV ? e1 : e0, e1});
     HADI_SYNC();
   }
   if constexpr (Feed::kTma) {
@@ -466,6 +466,7 @@ __global__ void __launch_bounds__(NT * DUO, MINB) hadi_douglas_kernel(const Hadi
   double* Ualloc = GLOBAL ? scratch + gl.U : reinterpret_cast<double*>(sbase + lay.U);
   w.U = Ualloc + HADI_HALO * w.ld + 1;
   w.Y = GLOBAL ? scratch + gl.Y : reinterpret_cast<double*>(sbase + lay.Y);
+  w.gstate = GLOBAL;
   w.ti = reinterpret_cast<double*>(sbase + lay.ti);
   w.tj = reinterpret_cast<double*>(sbase + lay.tj);
   w.divk = reinterpret_cast<int*>(sbase + lay.divk);

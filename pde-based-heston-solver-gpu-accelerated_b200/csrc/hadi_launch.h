@@ -127,7 +127,7 @@ int hadi_launch_douglas(const HadiLaunch& L, const HadiPlan& plan, int grid_ctas
 // defined in hadi_wide.cu: one solve spread over a team of co-resident CTAs (co-operative launch); HadiPlan::cluster
 // carries the team size, set per batch with hadi_wide_team().  HadiLaunch::counter must hold HADI_COUNTER_INTS zeroed ints.
 #define HADI_WIDE_VARIANT 9
-#define HADI_WIDE_MAX_ITEMS_DEFAULT 48   /* batches up to this size of global-state solves go to the wide kernel (twice as many on small grids) */
+#define HADI_WIDE_MAX_ITEMS_DEFAULT 40   /* batches up to this size of global-state solves go to the wide kernel (twice as many on small grids) */
 #define HADI_COUNTER_INTS 2048   /* work counter, cluster mailboxes, one barrier word per team (16 + 8 * team) */
 int hadi_wide_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj, HadiPlan* plan);
 int hadi_wide_team(int n_items, int sm_count, int m1, int m2);
