@@ -118,6 +118,38 @@ HADI_HD HadiNb hadi_win_nb(const HadiWin<UNR>& W, int k) {
   return n;
 }
 
+// Douglas explicit stage at node (j, i) from neighbour values and the current multiplier (hadi_phase_explicit, operation
+// for operation: A1 in the device order lower, main, upper)
+HADI_HD double hadi_nb_explicit(const HadiItem& it, const HadiView& w, const HadiNb& n, double lam_cur, double e0, double e1,
+                                int i, int j) {
+  const int m1 = w.m1, m2 = w.m2;
+  const double dt = it.dt, c = w.c;
+  const bool am = it.style == 1;
+  const double x = n.z0;
+  const double r0 = hadi_nb_a0(w, n, i, j);
+  double lo, ma, upc;
+  hadi_nb_a1c(w, i, j, lo, ma, upc);
+  const double r1 = lo * n.zm + ma * x + upc * n.zp;
+  const double r2 = hadi_nb_a2(w, n, j);
+  const bool is_b1 = (i + j == m1);
+  double y;
+  if (is_b1 || j == m2) {
+    const double b1v = it.bc ? 0.0 : (it.r_d - it.r_f) * hadi_ti(w, TI_S)[m1] * it.ef;
+    const double b1p = is_b1 ? b1v : 0.0;
+    const double b2p = (j == m2) ? hadi_ti(w, TI_B2V)[i] : 0.0;
+    const double bp_ = 0.0 + b1p + b2p;
+    double sum = r0 + r1 + r2 + bp_ * e0;
+    if (am) sum = sum + lam_cur;
+    y = x + dt * sum;
+    y = y + c * (b1p * e1 - (r1 + b1p * e0));
+  } else {
+    double sum = r0 + r1 + r2;
+    if (am) sum = sum + lam_cur;
+    y = x + dt * sum;
+    y = y - c * r1;
+  }
+  return y;
+}
 // host boundary vectors at node (j, i): b1 at index m1*(j+1) (= node (j, m1-j), quirk Q3), b2 on the
 // last v-row from i = 1 (src/BoundaryConditions.hpp:72,77)
 HADI_HD void hadi_cs_bounds(const HadiItem& it, const HadiView& w, int i, int j, double& b1p, double& b2p) {

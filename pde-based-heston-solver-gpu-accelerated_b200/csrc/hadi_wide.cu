@@ -114,35 +114,9 @@ __device__ __forceinline__ WideNb wide_nb(const double* X, int ld, int i, int j)
 // Douglas explicit stage (hadi_phase_explicit)
 __device__ __forceinline__ double wide_node_explicit(const HadiItem& it, const HadiView& w, double e0, double e1, int i,
                                                      int j) {
-  const int m1 = w.m1, m2 = w.m2;
-  const double dt = it.dt, c = w.c;
-  const bool am = it.style == 1;
   const WideNb n = wide_nb(w.U, w.ld, i, j);
-  const double x = n.z0;
-  const double r0 = hadi_nb_a0(w, n, i, j);
-  double lo, ma, upc;
-  hadi_nb_a1c(w, i, j, lo, ma, upc);
-  const double r1 = lo * n.zm + ma * x + upc * n.zp;
-  const double r2 = hadi_nb_a2(w, n, j);
-  const double lam_cur = am ? wld(w.lam + j * w.ld + i) : 0.0;
-  const bool is_b1 = (i + j == m1);
-  double y;
-  if (is_b1 || j == m2) {
-    const double b1v = it.bc ? 0.0 : (it.r_d - it.r_f) * hadi_ti(w, TI_S)[m1] * it.ef;
-    const double b1p = is_b1 ? b1v : 0.0;
-    const double b2p = (j == m2) ? hadi_ti(w, TI_B2V)[i] : 0.0;
-    const double bp_ = 0.0 + b1p + b2p;
-    double sum = r0 + r1 + r2 + bp_ * e0;
-    if (am) sum = sum + lam_cur;
-    y = x + dt * sum;
-    y = y + c * (b1p * e1 - (r1 + b1p * e0));
-  } else {
-    double sum = r0 + r1 + r2;
-    if (am) sum = sum + lam_cur;
-    y = x + dt * sum;
-    y = y - c * r1;
-  }
-  return y;
+  const double lam_cur = (it.style == 1) ? wld(w.lam + j * w.ld + i) : 0.0;
+  return hadi_nb_explicit(it, w, n, lam_cur, e0, e1, i, j);
 }
 // Craig-Sneyd family, predictor (hadi_cs_predict): keeps R0, R1, R2, Y0 of the node
 __device__ __forceinline__ double wide_node_predict(const HadiItem& it, const HadiView& w, const HadiCsView& cs, double e0,
