@@ -34,7 +34,10 @@ namespace {
 
 constexpr int kWideThreads = 512;
 constexpr int kWideWarps = kWideThreads / 32;
-constexpr int kCh = 4;   // nodes per register chunk of a chain
+#ifndef HADI_WIDE_KCH
+#define HADI_WIDE_KCH 4   /* measured on B200: 6 and 8 nodes per chunk are no faster (tools/dev_timing_wide.py) */
+#endif
+constexpr int kCh = HADI_WIDE_KCH;   // nodes per register chunk of a chain
 constexpr int kPad = 2 * kCh;   // the sweeps are unrolled by two chunks and prefetch one chunk ahead
 
 __device__ __forceinline__ double wld(const double* p) { return __ldcg(p); }
