@@ -20,4 +20,12 @@ HADI_FORCE_VARIANT=7 ncu --set full --clock-control none --import-source on -k r
     python tools/prof_large.py 1 20 > $OUT/prof_v7_$TAG.log 2>&1; echo "ncu variant 7 rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:hadi_wide_kernel -s 1 -c 1 -f -o $OUT/prof_v9_$TAG \
     python tools/prof_large.py 1 20 > $OUT/prof_v9_$TAG.log 2>&1; echo "ncu variant 9 (wide kernel, one solve) rc=$?"
-ls -la $OUT/prof_*$TAG.ncu-rep
+# text summaries on the box (gpurun copies back at most 64 MiB: the reports of variants 5 and 7 are summarised and dropped)
+python tools/ncu_summary.py launches $OUT/launches_$TAG.csv > $OUT/sum_launches_$TAG.txt 2>&1
+for v in "" _v5 _v7 _v9; do
+  python tools/ncu_summary.py full $OUT/prof${v}_$TAG.ncu-rep > $OUT/sum_full${v}_$TAG.txt 2>&1
+  python tools/ncu_lines.py $OUT/prof${v}_$TAG.ncu-rep 60 > $OUT/sum_lines${v}_$TAG.txt 2>&1
+done
+python tools/ncu_fp64_by_phase.py $OUT/prof_$TAG.ncu-rep 500 50 5151 72 > $OUT/sum_fp64_by_phase_$TAG.txt 2>&1
+rm -f $OUT/prof_v5_$TAG.ncu-rep $OUT/prof_v7_$TAG.ncu-rep
+ls -la $OUT/
