@@ -562,8 +562,8 @@ __global__ void __launch_bounds__(NT * DUO, MINB) hadi_douglas_kernel(const Hadi
     const HadiItem it = L.items[sg.item];
     if (!split) sg.n1 = it.N;
     HADI_TICK(0)
-    // state left by the CTA that ran steps 1..n0-1: wait for it (bounded: after two seconds, or if that CTA's
-    // guarded divisions left their range, this CTA solves the item from the payoff instead)
+    // state left by the CTA that ran steps 1..n0-1: wait for it (bounded: after 100 ms — fifty times a config-2 launch —
+    // or if that CTA's guarded divisions left their range, this CTA solves the item from the payoff instead)
     bool whole_exact = false;
     const double* hin = nullptr;
     if (sg.hin >= 0) {
@@ -575,7 +575,7 @@ __global__ void __launch_bounds__(NT * DUO, MINB) hadi_douglas_kernel(const Hadi
           asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(st) : "l"(L.hand_state + sg.hin) : "memory");
           if (st != HADI_HAND_PENDING) break;
           asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-          if (t1 - t0 > 2000000000ull) { st = HADI_HAND_BAD; break; }
+          if (t1 - t0 > 100000000ull) { st = HADI_HAND_BAD; break; }
           __nanosleep(200);
         }
         s_item = st;

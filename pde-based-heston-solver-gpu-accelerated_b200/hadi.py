@@ -6,6 +6,7 @@ behind the C ABI; there is no Python or CPU fallback — if the library (or a CU
 the calls fail loudly.
 """
 import ctypes as C
+import weakref
 import os
 
 import numpy as np
@@ -435,6 +436,10 @@ class Context:
 
     def close(self):
         if self._h:
+            # prepared batches hold pool buffers of this context: release them first (a Batch destroyed after its
+            # Context would hand the library a dangling pointer)
+            for b in list(getattr(self, "_batches", ())):
+                b.destroy()
             lib().hadi_destroy(self._h)
             self._h = None
 
@@ -557,6 +562,9 @@ class Batch:
                                               begin, end, C.byref(self._h)))
         self.n_items = lib().hadi_batch_num_items(self._h)
         self.values_per_item = lib().hadi_batch_values_per_item(self._h)
+        if not hasattr(ctx, "_batches"):
+            ctx._batches = weakref.WeakSet()
+        ctx._batches.add(self)
 
     def update_model(self, model):
         """Re-aim the prepared batch at new (kappa, eta, sigma, rho, V0); S0, r_d, r_f as at creation."""
