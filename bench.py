@@ -247,6 +247,27 @@ def lm_calibration(hadi, ctx, solo=None, world=1, rank=0, dist=None):
                 out[name]["strong_scaling_efficiency"] = round(one / (world * best), 4)
                 out[name]["equals_single_gpu"] = bool(r1["params"] == res["params"] and r1["final_error"] == res["final_error"])
             dist.barrier()
+        # opt-in solver-call schedule: the candidate is evaluated with its own Jacobian batch (one call per iteration,
+        # 6n solves instead of 7n); same parameters and errors bit for bit, fewer and fuller launches
+        sbest = None
+        for rep in range(3):
+            t0 = time.perf_counter()
+            sres = ctx.calibrate(hadi.make_model(**BASE), num, pts, n, market, 15, 0.1 * math.sqrt(n),
+                                 0.1 * (1.0 + math.log(n)), schedule=hadi.LM_SCHEDULE_SPECULATIVE)
+            ms = (time.perf_counter() - t0) * 1e3
+            sbest = ms if sbest is None else min(sbest, ms)
+        sgpu = sres["gpu_ms"]
+        if dist is not None:
+            import torch
+
+            tb = torch.tensor([sbest, sgpu], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+            sbest, sgpu = float(tb[0]), float(tb[1])
+        out[name]["speculative_schedule_optin"] = {
+            "wall_ms": round(sbest, 3), "gpu_ms": round(sgpu, 3), "iterations": sres["iterations"],
+            "pde_solves": sres["pde_solves"],
+            "equals_reference_schedule": bool(sres["params"] == res["params"] and sres["final_error"] == res["final_error"]
+                                              and sres["iterations"] == res["iterations"] and sres["lam"] == res["lam"])}
         try:   # golden trajectory of the reference itself (tests/golden/lm_more.json, oracle/make_golden.py more)
             G = json.load(open(os.path.join(ROOT, "tests", "golden", "lm_more.json")))["config3_" + name]
             out[name]["equals_reference"] = bool(out[name]["params"] == G["params"] and

@@ -168,9 +168,19 @@ int hadi_jacobian_batch(hadi_ctx* ctx, const hadi_model* model, const hadi_numer
  *            {base, +kappa, +eta, +sigma, +rho, +v0, -kappa, -eta, -sigma, -rho, -v0} */
 #define HADI_MODE_JACOBIAN_INTERP 2
 #define HADI_MODE_JACOBIAN_CENTRAL 3
+/* How hadi_calibrate_ex spends its solver calls.  REFERENCE is the reference's loop (src/heston_calibration.cpp:
+ * 2692-2831): Jacobian at the current point (6n solves), candidate prices (n solves), and after a rejected step the same
+ * Jacobian again.  SPECULATIVE evaluates the candidate with the Jacobian batch itself — its base column IS the
+ * candidate's prices — so that an accepted step already holds the next iteration's Jacobian, and keeps the Jacobian of
+ * the current point across rejected steps: one solver call per iteration instead of two, 6n solves per iteration
+ * instead of 7n, and the same parameters, errors and lambda bit for bit (every solve is the same solve; only
+ * hadi_lm_result::pde_solves differs). */
+#define HADI_LM_SCHEDULE_REFERENCE 0
+#define HADI_LM_SCHEDULE_SPECULATIVE 1
 typedef struct {
   int mode;        /* HADI_MODE_JACOBIAN | _INTERP | _CENTRAL */
   double eps[5];   /* bump per parameter (kappa, eta, sigma, rho, v0); the reference uses 1e-6 for all */
+  int schedule;    /* HADI_LM_SCHEDULE_* (hadi_calibrate_ex only) */
 } hadi_jacobian_options;
 /* Work items are options (PRICE) or option x {base, kappa, eta, sigma, rho, v0} (JACOBIAN), item
  * index = option*6 + column.  [item_begin, item_end) selects the slice this context solves

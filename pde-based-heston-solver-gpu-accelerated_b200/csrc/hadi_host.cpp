@@ -1200,7 +1200,7 @@ int hadi_price_batch(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics
 
 int hadi_jacobian_batch(hadi_ctx* ctx, const hadi_model* model, const hadi_numerics* num, int n,
                         const hadi_point* points, double eps, double* J, double* base_prices) try {
-  hadi_jacobian_options jo;
+  hadi_jacobian_options jo{};
   jo.mode = HADI_MODE_JACOBIAN;
   for (int c = 0; c < 5; ++c) jo.eps[c] = eps;
   return hadi_jacobian_batch_ex(ctx, model, num, n, points, &jo, J, base_prices);
@@ -1208,6 +1208,7 @@ int hadi_jacobian_batch(hadi_ctx* ctx, const hadi_model* model, const hadi_numer
 
 static bool valid_jopt(const hadi_jacobian_options* jo) {
   if (!jo) return false;
+  if (jo->schedule != HADI_LM_SCHEDULE_REFERENCE && jo->schedule != HADI_LM_SCHEDULE_SPECULATIVE) return false;
   if (jo->mode != HADI_MODE_JACOBIAN && jo->mode != HADI_MODE_JACOBIAN_INTERP && jo->mode != HADI_MODE_JACOBIAN_CENTRAL)
     return false;
   for (int c = 0; c < 5; ++c)
@@ -1476,7 +1477,7 @@ int hadi_calibrate(hadi_ctx* ctx, const hadi_model* initial, const hadi_numerics
                    const hadi_point* points, const double* market, const hadi_lm_options* opt,
                    const hadi_comm* comm, hadi_lm_result* res) try {
   if (!opt) return HADI_ERR_ARG;
-  hadi_jacobian_options jo;
+  hadi_jacobian_options jo{};
   jo.mode = HADI_MODE_JACOBIAN;
   for (int c = 0; c < 5; ++c) jo.eps[c] = opt->eps;
   return hadi_calibrate_ex(ctx, initial, num, n, points, market, opt, &jo, comm, res);
@@ -1509,12 +1510,17 @@ int hadi_calibrate_ex(hadi_ctx* ctx, const hadi_model* initial, const hadi_numer
   int rc = sharded_create(ctx, &cur, num, n, points, jo->mode, jo->eps, comm, &sb_jac);
   if (rc == HADI_OK) rc = sharded_create(ctx, &cur, num, n, points, HADI_MODE_PRICE, kNoEps, comm, &sb_price);
   if (rc != HADI_OK) return rc;
+  const bool speculative = jo->schedule == HADI_LM_SCHEDULE_SPECULATIVE;
+  std::vector<double> cand_vals(speculative ? vals.size() : 0);
+  bool have_jacobian = false;   // speculative schedule: vals already holds the item values at `cur`
   for (int iter = 0; iter < opt->max_iter && !converged; ++iter) {
     float ms = 0.f;
-    rc = sharded_solve(ctx, &sb_jac, iter == 0 ? nullptr : &cur, vals.data(), &ms);
-    if (rc != HADI_OK) return rc;
-    gpu_ms += ms;
-    solves += jcols * n;
+    if (!have_jacobian) {
+      rc = sharded_solve(ctx, &sb_jac, iter == 0 ? nullptr : &cur, vals.data(), &ms);
+      if (rc != HADI_OK) return rc;
+      gpu_ms += ms;
+      solves += jcols * n;
+    }
     int blo, bhi;
     double bw = 0.0;
     hadi_jacobian_v0_weight(num->m2, cur.V0, jo->eps[4], &blo, &bhi, &bw);
@@ -1545,11 +1551,21 @@ int hadi_calibrate_ex(hadi_ctx* ctx, const hadi_model* initial, const hadi_numer
       iters = iter + 1;
       break;
     }
-    rc = sharded_solve(ctx, &sb_price, &nw, nv.data(), &ms);
-    if (rc != HADI_OK) return rc;
-    gpu_ms += ms;
-    solves += n;
-    for (int k = 0; k < n; ++k) newp[points[k].global_index] = nv[k];
+    if (speculative) {
+      // the candidate's prices are the base column of ITS Jacobian batch: solve that, and keep it if the step is accepted
+      rc = sharded_solve(ctx, &sb_jac, &nw, cand_vals.data(), &ms);
+      if (rc != HADI_OK) return rc;
+      gpu_ms += ms;
+      solves += jcols * n;
+      const size_t per_option = (size_t)jcols * values_per_item(jo->mode);
+      for (int k = 0; k < n; ++k) newp[points[k].global_index] = cand_vals[per_option * k];
+    } else {
+      rc = sharded_solve(ctx, &sb_price, &nw, nv.data(), &ms);
+      if (rc != HADI_OK) return rc;
+      gpu_ms += ms;
+      solves += n;
+      for (int k = 0; k < n; ++k) newp[points[k].global_index] = nv[k];
+    }
     double new_err = 0.0;
     for (int i = 0; i < n; ++i) {
       const double rr = market[i] - newp[i];
@@ -1558,9 +1574,11 @@ int hadi_calibrate_ex(hadi_ctx* ctx, const hadi_model* initial, const hadi_numer
     if (new_err < cur_err) {
       cur = nw;
       lambda = std::max(lambda / 10.0, 1e-7);
+      if (speculative) vals.swap(cand_vals);   // the Jacobian of the next iteration is already here
     } else {
       lambda = std::min(lambda * 10.0, 1e7);
     }
+    have_jacobian = speculative;   // accepted: the candidate's batch; rejected: the Jacobian at `cur` is still valid
     final_error = std::min(new_err, cur_err);
     iters = iter + 1;
   }

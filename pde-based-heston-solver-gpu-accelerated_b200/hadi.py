@@ -72,12 +72,16 @@ class LmResult(C.Structure):
 
 
 class JacobianOptions(C.Structure):
-    _fields_ = [("mode", C.c_int), ("eps", C.c_double * 5)]
+    _fields_ = [("mode", C.c_int), ("eps", C.c_double * 5), ("schedule", C.c_int)]
 
 
-def make_jacobian_options(mode=MODE_JACOBIAN, eps=1e-6):
+LM_SCHEDULE_REFERENCE, LM_SCHEDULE_SPECULATIVE = 0, 1
+
+
+def make_jacobian_options(mode=MODE_JACOBIAN, eps=1e-6, schedule=LM_SCHEDULE_REFERENCE):
     jo = JacobianOptions()
     jo.mode = mode
+    jo.schedule = schedule
     e = np.broadcast_to(np.asarray(eps, dtype=np.float64), (5,))
     for k in range(5):
         jo.eps[k] = float(e[k])
@@ -533,15 +537,15 @@ class Context:
         return Batch(self, model, num, pts, n, mode, eps, begin, end)
 
     def calibrate(self, model, num, pts, n, market, max_iter, tol, delta_tol, lambda0=0.01, eps=1e-6, comm=None,
-                  jac_mode=None):
+                  jac_mode=None, schedule=LM_SCHEDULE_REFERENCE):
         market = np.ascontiguousarray(market, dtype=np.float64)
         opt = LmOptions(max_iter, tol, delta_tol, lambda0, float(np.atleast_1d(eps)[0]))
         res = LmResult()
-        if jac_mode is None:
+        if jac_mode is None and schedule == LM_SCHEDULE_REFERENCE:
             self._check(lib().hadi_calibrate(self._h, C.byref(model), C.byref(num.num), n, pts, _d(market),
                                              C.byref(opt), None if comm is None else C.byref(comm), C.byref(res)))
         else:
-            jo = make_jacobian_options(jac_mode, eps)
+            jo = make_jacobian_options(MODE_JACOBIAN if jac_mode is None else jac_mode, eps, schedule)
             self._check(lib().hadi_calibrate_ex(self._h, C.byref(model), C.byref(num.num), n, pts, _d(market),
                                                 C.byref(opt), C.byref(jo),
                                                 None if comm is None else C.byref(comm), C.byref(res)))

@@ -687,6 +687,52 @@ def test_lm_shipped_american_dividend_driver_rejects(hadi, ctx):
     _lm_against(hadi, ctx, G, K, T, N, market, divs)
 
 
+def test_lm_speculative_schedule_is_the_same_calibration(hadi, ctx):
+    """HADI_LM_SCHEDULE_SPECULATIVE: the candidate of every LM step is evaluated with its own Jacobian batch (whose base
+    column is the candidate's prices) and the Jacobian of the current point survives rejected steps — one solver call
+    and 6n solves per iteration instead of two calls and 7n.  Parameters, error, lambda, step norm and iteration count
+    are those of the reference schedule bit for bit: on the 18-iteration American + dividend driver, which rejects
+    steps, on the clamped European driver, and with the interpolated-V0 Jacobian."""
+    G = golden("lm_more.json")
+    cases = []
+    g = G["shipped_american_dividend"]
+    K, T, N = [], [], []
+    for Tm in (1.0, 1.5, 2.0):
+        for i in range(60):
+            K.append(100.0 * 0.7 + i * 1)
+            T.append(Tm)
+            N.append(max(20, int(Tm * 20)))
+    kap, eta, sig, rho, v0 = g["market_params"]
+    divs = tuple(g["divs"])
+    num = hadi.make_numerics(50, 25, 0.8, hadi.AMERICAN, hadi.CALL, hadi.DOUGLAS, divs)
+    pts, n = hadi.make_points(K, T, N)
+    market = ctx.price_batch(hadi.make_model(**dict(BASE, kappa=kap, eta=eta, sigma=sig, rho=rho, V0=v0)), num, pts, n)["prices"].copy()
+    cases.append((g, num, pts, n, market, None))
+    g3 = G["config3_51x26"]
+    mats = [1.0 + i * 0.25 if i < 8 else 3.0 + (i - 8) * 0.5 for i in range(10)]
+    K3 = [95.0 + 1.0 * s for Tm in mats for s in range(10)]
+    T3 = [Tm for Tm in mats for s in range(10)]
+    N3 = [max(20, int(t * 20)) for t in T3]
+    pts3, n3 = hadi.make_points(K3, T3, N3)
+    market3 = [hadi.bs_call(100.0, k, 0.025, 0.2, t) for k, t in zip(K3, T3)]
+    cases.append((g3, hadi.make_numerics(50, 25, 0.8), pts3, n3, market3, None))
+    cases.append((g3, hadi.make_numerics(50, 25, 0.8), pts3, n3, market3, hadi.MODE_JACOBIAN_INTERP))
+    for (g, num, pts, n, market, jm) in cases:
+        ref = ctx.calibrate(hadi.make_model(**BASE), num, pts, n, market, g["max_iter"], g["tol"], g["delta_tol"], jac_mode=jm)
+        before = ctx.kernel_launches
+        spec = ctx.calibrate(hadi.make_model(**BASE), num, pts, n, market, g["max_iter"], g["tol"], g["delta_tol"],
+                             jac_mode=jm, schedule=hadi.LM_SCHEDULE_SPECULATIVE)
+        for key in ("params", "final_error", "lam", "delta_norm", "iterations", "converged"):
+            assert spec[key] == ref[key], key
+        if jm is None:
+            assert [repr(float(x)) for x in spec["params"]] == g["params"] and repr(float(spec["final_error"])) == g["final_error"]
+        # one solver call per iteration that evaluates a candidate, plus the first Jacobian
+        its = ref["iterations"]
+        evaluated = its - 1 if ref["converged"] else its
+        assert ctx.kernel_launches - before == 1 + evaluated
+        assert spec["pde_solves"] < ref["pde_solves"]
+
+
 def test_rerun_counter_is_visible_without_profiling(hadi, monkeypatch):
     """hadi_exact_reruns: 0 on option data; when every fast pass is declared out of range (test hook) every solve of
     the batch is counted, through the one-call entry point and through a prepared batch."""
