@@ -3,8 +3,9 @@
 // What bounds ONE large solve (401 x 201, 200 steps, Craig-Sneyd) is not memory or arithmetic throughput but the
 // dependent FP64 chain of its line solves: a forward / backward Thomas sweep along 400 nodes is 400 x (16 + 40)
 // cycles whoever runs it, and bit parity with the reference forbids re-associating it.  The lines of one sweep are
-// independent, so the fastest schedule gives every line its own thread ON ITS OWN WARP SCHEDULER, with every operand
-// of the chain already in shared memory, and lets all other work of the step disappear behind it:
+// independent, so the fastest schedule gives every line its own thread (the lines of a CTA packed into at most two warps
+// per scheduler, one lane each), with every operand of the chain already in shared memory, and lets all other work of
+// the step disappear behind it:
 //
 //   * rows (A1 sweeps) are dealt round-robin to the CTAs of the team, columns (A2 sweeps) in contiguous blocks;
 //   * the point-wise stage that FEEDS a sweep is evaluated by the CTA that owns the line, straight into the
@@ -18,11 +19,11 @@
 //     scratch block of the team and are read with ld.global.cg (other SMs write them between barriers).
 //
 // Arithmetic: the expressions of hadi_phases.cuh / hadi_phases_cs.cuh, operation for operation (the tables and the
-// factorisation ARE those functions); results are bit-identical to every other variant.  Guarded divisions use the
-// in-line IEEE fallback (hadi_div<false, true>), so there is no re-solve pass.
+// factorisation ARE those functions); results are bit-identical to every other variant.  A guarded division that leaves
+// its operand range is redone with the IEEE division, one chunk of the chain at a time, so there is no re-solve pass.
 //
-// Replaces, for batches of a few solves, the thread-block-cluster kernel of round 1
-// (hadi_cluster_kernel, 8 CTAs, every phase through L2): 401 x 201 x 200 Craig-Sneyd 68 ms -> see DESIGN.md section 7.
+// Replaces, for batches of a few solves, the thread-block-cluster kernel of round 1 (hadi_cluster_kernel, 8 CTAs, every
+// phase through L2): 401 x 201 x 200 Craig-Sneyd 67.7 -> 12.3 ms for one solve.
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdlib>
@@ -506,7 +507,9 @@ __global__ void __launch_bounds__(kWideThreads, 1) hadi_wide_kernel(const HadiLa
   w.tj = sp; sp += (size_t)TJ_COUNT * w.n2;
   w.divk = reinterpret_cast<int*>(sp); sp += w.n1 / 2;   // n1 ints (n1 is a multiple of four)
   double* arena = sp;
-  const int arena_doubles = L.dbg_phase;   // set by hadi_launch_wide: doubles of shared memory behind the tables
+  unsigned dyn_smem;
+  asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_smem));
+  const int arena_doubles = (int)((dyn_smem - (unsigned)((char*)arena - (char*)smem)) / sizeof(double));   // what is left behind the tables
   double* scratch = L.scratch + (size_t)team * L.scratch_stride;
   const HadiScratchLayout gl = hadi_scratch_layout(m1, m2, w.ld, w.pj, true, L.scheme >= 1);
   double* Ualloc = scratch + gl.U;
@@ -705,8 +708,6 @@ int hadi_launch_wide(const HadiLaunch& L_in, const HadiPlan& plan, int grid_ctas
   if (G < 1 || grid_ctas % G != 0) return (int)cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute((const void*)hadi_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes);
   if (e != cudaSuccess) return (int)e;
-  L.dbg_phase = (int)((plan.smem_bytes - wide_table_bytes(L.n1, L.n2)) / sizeof(double));   // arena size, doubles
-  L.dbg_step = 0;
   void* args[] = {(void*)&L, (void*)&G};
   // co-operative launch: the runtime refuses a grid whose CTAs cannot all be resident (the team barrier needs them)
   e = cudaLaunchCooperativeKernel((const void*)hadi_wide_kernel, dim3((unsigned)grid_ctas), dim3(kWideThreads), args, plan.smem_bytes,
