@@ -633,8 +633,9 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
   HadiPlan plan;
   const char* forced_variant = getenv("HADI_FORCE_VARIANT");
   const int n_it_plan = (item_end < 0 ? n * n_columns(mode) : item_end) - item_begin;
+  const bool many_items = n_it_plan >= 6 * 148;   // fills the slots of the small-CTA instantiation (51 x 26: variant 11)
   const auto plan_key = std::make_tuple(num->m1, num->m2, num->scheme,
-                                        (int)(n_it_plan * HADI_CLUSTER <= 148 && num->num_dividends == 0),
+                                        (int)(n_it_plan * HADI_CLUSTER <= 148 && num->num_dividends == 0) + 2 * (int)many_items,
                                         std::string(forced_variant ? forced_variant : "") + "|" +
                                             std::string(getenv("HADI_NO_DUO") ? getenv("HADI_NO_DUO") : ""));
   const auto plan_hit = ctx->plans.find(plan_key);
@@ -649,7 +650,7 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
     // jump keeps per-CTA tables and stays on the one-CTA-per-solve kernels)
     const int n_it = (item_end < 0 ? n * n_columns(mode) : item_end) - item_begin;
     const bool few = n_it * HADI_CLUSTER <= 148 && num->num_dividends == 0;
-    int prc = hadi_douglas_plan(ctx->device, m1, m2, g.ld, g.n1, g.n2, g.pj, cs, &plan, few);
+    int prc = hadi_douglas_plan(ctx->device, m1, m2, g.ld, g.n1, g.n2, g.pj, cs, &plan, few, many_items);
     // grids beyond shared memory run on the global-state kernel (working set in L2-resident scratch)
     if (prc < 0 && !cs) prc = hadi_douglas_plan(ctx->device, m1, m2, g.ld, g.n1, g.n2, g.pj, true, &plan, few);
     // a Douglas grid that only the global-state kernel takes: same choice between one CTA and one cluster per solve
@@ -835,7 +836,7 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
     const char* ns = getenv("HADI_NO_SPLIT");
     const char* su = getenv("HADI_SPLIT_SETUP");
     const double setup = su ? atof(su) : 1.5;
-    if (!(ns && atoi(ns) != 0) && !plan.global_state && plan.cluster <= 1 && (plan.variant <= 3 || plan.variant == 8) && !getenv("HADI_MAX_CTAS"))
+    if (!(ns && atoi(ns) != 0) && !plan.global_state && plan.cluster <= 1 && (plan.variant <= 3 || plan.variant == 8 || plan.variant == 11) && !getenv("HADI_MAX_CTAS"))
       use_split = build_split_schedule(items, slots, setup, &sched);
   }
 

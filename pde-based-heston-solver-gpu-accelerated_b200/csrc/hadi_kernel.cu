@@ -822,6 +822,9 @@ __global__ void __cluster_dims__(HADI_CLUSTER, 1, 1) __launch_bounds__(NT, 1) ha
 // 0: 101 x 51 nodes (BASELINE configs 1, 2, 5): 320 threads = 3 row-chunks x 101 columns (+17),
 //    2 CTAs/SM, <= 102 registers (no spills: L1 is all but gone at this shared-memory carve-out)
 // 1:  51 x 26 nodes (the reference's own test / benchmark grid): 256 threads = 5 x 51 (+1), 3 CTAs/SM
+// 11: the same grid with 128 threads = 2 x 51 (+26) and 6 CTAs/SM: a solve takes 40 % longer, twice as many fill the chain
+//     phases of the others — 9 to 12 % more throughput on batches of two thousand solves (tools/time_51x26.py); chosen by
+//     hadi_douglas_plan for batches that fill its 888 slots
 // 2: any grid with m1+1 <= 416 that fits shared memory, run-time dimensions, direct factor loads
 // 3: any grid with m1+1 <= 1024 that fits shared memory, run-time dimensions, one CTA per SM
 // 5: any grid with m1+1 <= 512: U and Y in L2-resident global scratch, tables in shared memory, TMA ring for
@@ -838,6 +841,10 @@ __global__ void __cluster_dims__(HADI_CLUSTER, 1, 1) __launch_bounds__(NT, 1) ha
 #ifndef HADI_FEED1
 #define HADI_FEED1 3
 #endif
+#ifndef HADI_V1_NT
+#define HADI_V1_NT 256     /* 51 x 26: threads per CTA and CTAs per SM */
+#define HADI_V1_MINB 3
+#endif
 #ifndef HADI_DUO_NT
 #define HADI_DUO_NT 320   /* threads per team of the duo kernel (2 x 256 threads with 128 registers each measured slower) */
 #endif
@@ -853,7 +860,8 @@ __global__ void __cluster_dims__(HADI_CLUSTER, 1, 1) __launch_bounds__(NT, 1) ha
 // X(id, threads per team, min CTAs/SM, m1, m2, feed, global state, teams per CTA)
 #define HADI_VARIANTS(X)                    \
   X(0, 320, 2, 100, 50, HADI_FEED0, false, 1) \
-  X(1, 256, 3, 50, 25, HADI_FEED1, false, 1)  \
+  X(1, HADI_V1_NT, HADI_V1_MINB, 50, 25, HADI_FEED1, false, 1)  \
+  X(11, 128, 6, 50, 25, HADI_FEED1, false, 1)  \
   X(2, 416, 2, 0, 0, 0, false, 1)          \
   X(3, 1024, 1, 0, 0, 0, false, 1)         \
   X(4, 320, 2, 100, 50, 4, false, 1)       \
@@ -877,7 +885,7 @@ const VariantInfo* variants() {
   };
   return v;
 }
-constexpr int kNumVariants = 7 + HADI_DUO;   // entries of the table above
+constexpr int kNumVariants = 8 + HADI_DUO;   // entries of the table above
 constexpr int kClusterVariant = 7;   // hadi_cluster_kernel: one solve per thread-block cluster
 constexpr int kDuoVariant = 8;
 const VariantInfo* variant_by_id(int id) {
@@ -891,7 +899,7 @@ constexpr int kClusterThreads = 256; // few threads, many registers: the generic
 }  // namespace
 
 int hadi_douglas_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj, bool need_global, HadiPlan* plan,
-                      bool want_cluster) {
+                      bool want_cluster, bool many) {
   int max_smem = 0, sms = 0;
   cudaError_t e = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   if (e != cudaSuccess) return (int)e;
@@ -940,6 +948,9 @@ int hadi_douglas_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj
   }
   for (int k = 0; k < kNumVariants && pick < 0; ++k) {
     if (v[k].duo > 1 && !(force && atoi(force) == v[k].id)) continue;
+    // two instantiations for the 51 x 26 grid: the one with more, smaller CTAs only when the batch fills them
+    if (!force && v[k].id == 1 && many) continue;
+    if (!force && v[k].id == 11 && !many) continue;
     if (eligible(v[k], &smem)) pick = k;
   }
   if (pick < 0) return -1;

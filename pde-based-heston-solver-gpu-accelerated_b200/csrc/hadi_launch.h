@@ -121,7 +121,7 @@ HADI_HD HadiScratchLayout hadi_scratch_layout(int m1, int m2, int ld, int pj, bo
 // defined in hadi_kernel.cu; return 0 or a cudaError_t
 #define HADI_CLUSTER 8
 int hadi_douglas_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj, bool need_global, HadiPlan* plan,
-                      bool want_cluster = false);
+                      bool want_cluster = false, bool many = false);
 int hadi_launch_douglas(const HadiLaunch& L, const HadiPlan& plan, int grid_ctas, void* stream);
 
 // defined in hadi_wide.cu: one solve spread over a team of co-resident CTAs (co-operative launch); HadiPlan::cluster

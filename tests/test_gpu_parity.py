@@ -733,6 +733,31 @@ def test_lm_speculative_schedule_is_the_same_calibration(hadi, ctx):
         assert spec["pde_solves"] < ref["pde_solves"]
 
 
+def test_small_cta_instantiation_for_large_51x26_batches(hadi, ctx, oracle, monkeypatch):
+    """Variant 11 (51x26 grid, 128 threads, six CTAs per SM) is what the planner picks for batches that fill its 888
+    slots; it must be the same arithmetic as variant 1 (256 threads, three per SM): American + dividends on the split
+    schedule, bit-equal prices for every item, full grids against the oracle."""
+    mdl = hadi.make_model(**BASE)
+    num = hadi.make_numerics(50, 25, 0.8, hadi.AMERICAN, hadi.CALL, hadi.DOUGLAS, DIVS)
+    K = [80.0 + 0.04 * k for k in range(1000)]
+    Ns = [10 + (k % 4) for k in range(1000)]
+    pts, n = hadi.make_points(K, 1.0, Ns)
+    bt = ctx.batch(mdl, num, pts, n)
+    assert bt.kernel_info[0] == 11
+    bt.destroy()
+    pts_few, n_few = hadi.make_points(K[:500], 1.0, Ns[:500])
+    bt = ctx.batch(mdl, num, pts_few, n_few)
+    assert bt.kernel_info[0] == 1
+    bt.destroy()
+    a = ctx.price_batch(mdl, num, pts, n, want_U=True, want_lambda=True)
+    monkeypatch.setenv("HADI_FORCE_VARIANT", "1")
+    b = ctx.price_batch(mdl, num, pts, n)
+    assert np.array_equal(a["prices"], b["prices"])
+    for k in (0, 499, 999):
+        o = oracle.solve(K[k], Ns[k], 1.0 / Ns[k], m1=50, m2=25, theta=0.8, style=1, divs=DIVS, **BASE)
+        assert a["prices"][k] == o["price"] and np.array_equal(a["U"][k], o["U"]) and np.array_equal(a["lambda"][k], o["lambda"])
+
+
 def test_rerun_counter_is_visible_without_profiling(hadi, monkeypatch):
     """hadi_exact_reruns: 0 on option data; when every fast pass is declared out of range (test hook) every solve of
     the batch is counted, through the one-call entry point and through a prepared batch."""
