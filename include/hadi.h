@@ -25,6 +25,12 @@
  *   BlackScholes::generate_market_data{,_with_dividends}   src/bs.hpp:58-112    hadi_market_prices, hadi_dividend_adjusted_spot
  *   implied-vol post-processing and CSV export of the LM drivers                hadi_implied_vols, hadi_write_calibration_csv
  *       src/heston_calibration.cpp:436-511, 2853-2923
+ *   CS_scheme_shuffled / MCS_scheme_shuffled (host solver)                      hadi_price_batch with hadi_numerics::scheme
+ *       src/solver.hpp:781-907, 917-1075                                        (large grids: the wide kernel)
+ *   ConvergenceExporter::testWithRelatedGridSizes / exportToCSV                 hadi_convergence_study,
+ *       src/solver.cpp:50-295                                                   hadi_write_convergence_csv
+ *   (no counterpart) the LM loop on one solver call per iteration               hadi_calibrate_ex with
+ *                                                                               HADI_LM_SCHEDULE_SPECULATIVE (opt-in)
  *
  * Conventions
  *   - Plain C types only.  All pointers are HOST pointers unless the name ends in _dev.
