@@ -671,7 +671,10 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
     // measured on B200 (tools/time_wide.py): 401 x 201 Craig-Sneyd breaks even with the one-CTA kernel near 40 solves,
     // 101 x 51 near 80 (the smaller the grid, the more of its lines fit one CTA's shared memory at once)
     const int wide_max = wm ? atoi(wm) : (P > 16384 ? HADI_WIDE_MAX_ITEMS_DEFAULT : 2 * HADI_WIDE_MAX_ITEMS_DEFAULT);
-    if (n_it_plan >= 1 && (forced_wide || (!forced_variant && plan.global_state && n_it_plan <= wide_max))) {
+    // Grids so small that the A2 assembly scratch (TS_COUNT rows of n2 doubles) does not fit the Y array the other
+    // kernels borrow for it (roughly m1 < 20) also go to the wide kernel, whatever the batch: it has its own arena.
+    const bool tiny_grid = (size_t)TS_COUNT * g.n2 > (size_t)(m2 + 1) * g.ld;
+    if (n_it_plan >= 1 && (forced_wide || tiny_grid || (!forced_variant && plan.global_state && n_it_plan <= wide_max))) {
       const auto wkey = std::make_tuple(num->m1, num->m2, num->scheme, 2, std::string("wide"));
       auto wh = ctx->plans.find(wkey);
       if (wh == ctx->plans.end()) {
@@ -682,7 +685,7 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
       if (wh->second.first == 0) {
         plan = wh->second.second;
         plan.cluster = hadi_wide_team(n_it_plan, plan.sm_count, m1, m2);
-      } else if (forced_wide) {
+      } else if (forced_wide || tiny_grid) {
         return fail(ctx, HADI_ERR_SMEM, "the wide kernel does not take this grid");
       }
     }
