@@ -640,6 +640,8 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
                                             std::string(getenv("HADI_NO_DUO") ? getenv("HADI_NO_DUO") : ""));
   const auto plan_hit = ctx->plans.find(plan_key);
   const bool forced_wide = forced_variant && atoi(forced_variant) == HADI_WIDE_VARIANT;
+  if (forced_variant && atoi(forced_variant) == 7 && num->num_dividends > 0)   // the planner never pairs them; a forced run must not skip the jumps silently
+    return fail(ctx, HADI_ERR_ARG, "the cluster kernel (variant 7) does not take dividend jumps");
   if (forced_wide) {
     plan.global_state = true;   // filled in below
   } else if (plan_hit != ctx->plans.end() && plan_hit->second.first == 0) {

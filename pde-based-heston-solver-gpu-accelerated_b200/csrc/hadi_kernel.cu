@@ -772,7 +772,7 @@ __global__ void __cluster_dims__(HADI_CLUSTER, 1, 1) __launch_bounds__(NT, 1) ha
   w.m1 = m1; w.m2 = m2; w.P = (m1 + 1) * (m2 + 1);
   w.ld = hadi_geo_ld(m1); w.n1 = hadi_geo_n1(m1); w.n2 = hadi_geo_n2(m2); w.pj = hadi_geo_pj(m2);
   w.line_mul = HADI_CLUSTER; w.line_off = rank;
-  w.ts_off = rank * TS_COUNT * w.n2;   // (8 x 18 x n2 doubles: far inside Y for any grid the kernel is chosen for)
+  // per-CTA A2 assembly scratch: its own region of the scratch block (hadi_ts() addresses it relative to Y)
   const HadiSmemLayout lay = hadi_smem_layout(m1, m2, w.ld, w.n1, w.n2, w.pj, false, true);
   char* sbase = reinterpret_cast<char*>(smem);
   double* scratch = L.scratch + (size_t)cid * L.scratch_stride;
@@ -780,6 +780,7 @@ __global__ void __cluster_dims__(HADI_CLUSTER, 1, 1) __launch_bounds__(NT, 1) ha
   double* Ualloc = scratch + gl.U;
   w.U = Ualloc + HADI_HALO * w.ld + 1;
   w.Y = scratch + gl.Y;
+  w.ts_off = (int)(gl.ts - gl.Y) + rank * TS_COUNT * w.n2;
   w.ti = reinterpret_cast<double*>(sbase + lay.ti);
   w.tj = reinterpret_cast<double*>(sbase + lay.tj);
   w.divk = reinterpret_cast<int*>(sbase + lay.divk);

@@ -94,8 +94,9 @@ HADI_HD HadiSmemLayout hadi_smem_layout(int m1, int m2, int ld, int n1, int n2, 
 }
 // per-CTA global scratch: fM [m1][pj], fB [m1][2*pj], lambda [m2+1][ld]; the global-state kernel adds
 // U (with halo) and Y, and for Craig-Sneyd Y0, R0, R1, R2 — every array starts on a 128-byte boundary
+#define HADI_CLUSTER 8
 struct HadiScratchLayout {
-  size_t fM, fB, lam, U, Y, Y0, R0, R1, R2, mail, total;   // offsets in doubles
+  size_t fM, fB, lam, U, Y, Y0, R0, R1, R2, ts, mail, total;   // offsets in doubles
 };
 HADI_HD HadiScratchLayout hadi_scratch_layout(int m1, int m2, int ld, int pj, bool global_state, bool cs) {
   HadiScratchLayout s;
@@ -113,13 +114,15 @@ HADI_HD HadiScratchLayout hadi_scratch_layout(int m1, int m2, int ld, int pj, bo
   s.R0 = off; if (cs) off += arr; off = (off + 15) & ~size_t(15);
   s.R1 = off; if (cs) off += arr; off = (off + 15) & ~size_t(15);
   s.R2 = off; if (cs) off += arr; off = (off + 15) & ~size_t(15);
+  // cluster kernel: one A2 assembly scratch region per CTA (TS_COUNT rows of n2 doubles).  Round 1 kept them inside Y,
+  // which they overran on grids below about 35 s-nodes (into the mailbox behind the arrays: garbage results).
+  s.ts = off; if (global_state) off += (size_t)HADI_CLUSTER * TS_COUNT * hadi_geo_n2(m2); off = (off + 15) & ~size_t(15);
   s.mail = off; off += 16;   // cluster kernel: work-item mailbox and vote word
   s.total = (off + 31) & ~size_t(31);
   return s;
 }
 
 // defined in hadi_kernel.cu; return 0 or a cudaError_t
-#define HADI_CLUSTER 8
 int hadi_douglas_plan(int device, int m1, int m2, int ld, int n1, int n2, int pj, bool need_global, HadiPlan* plan,
                       bool want_cluster = false, bool many = false);
 int hadi_launch_douglas(const HadiLaunch& L, const HadiPlan& plan, int grid_ctas, void* stream);
