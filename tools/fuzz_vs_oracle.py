@@ -18,6 +18,8 @@ kinds = {}
 while time.time() - t0 < budget:
     m1 = int(rng.choice([rng.integers(6, 40), rng.integers(40, 140), rng.integers(140, 330)], p=[0.3, 0.5, 0.2]))
     m2 = int(rng.integers(4, min(m1, 90) + 1))
+    if os.environ.get("FUZZ_LARGE"):   # grids beyond shared memory (one-CTA, 1024-thread and wide kernels)
+        m1 = int(rng.integers(330, 760)); m2 = int(rng.integers(40, 160))
     scheme = int(rng.choice([0, 0, 0, 1, 2, 3]))
     style = int(rng.integers(0, 2)) if scheme == 0 else 0
     put = int(rng.integers(0, 2))
@@ -28,9 +30,11 @@ while time.time() - t0 < budget:
         dates = np.sort(rng.uniform(0.05, 0.95, nd))
         divs = (list(dates), list(rng.uniform(0.0, 1.0, nd)), list(rng.uniform(0.0, 0.03, nd)))
     div_all = int(rng.integers(0, 2)) if nd else 0
-    N = int(rng.integers(1, 9))
+    N = int(rng.integers(1, 4 if os.environ.get("FUZZ_LARGE") else 9))
     T = float(rng.choice([0.25, 1.0, 2.0]))
-    base = dict(S0=100.0, V0=float(rng.choice([0.04, 0.09])), r_d=0.025, r_f=float(rng.choice([0.0, 0.01])),
+    theta = float(rng.choice([0.5, 0.8, 0.8, 1.0]))
+    base = dict(S0=float(rng.choice([100.0, 100.0, 80.0, 123.4])), V0=float(rng.choice([0.04, 0.09, 0.0225])),
+                r_d=float(rng.choice([0.025, 0.025, 0.0, 0.06])), r_f=float(rng.choice([0.0, 0.01])),
                 rho=float(rng.uniform(-0.9, 0.3)), sigma=float(rng.uniform(0.1, 0.6)), kappa=float(rng.uniform(0.5, 3.0)),
                 eta=float(rng.uniform(0.02, 0.1)))
     nopt = int(rng.choice([1, 2, 5]))
@@ -41,7 +45,7 @@ while time.time() - t0 < budget:
     Ks = [float(k) for k in rng.uniform(80.0, 120.0, nopt)]
     mdl = hadi.make_model(**base)
     try:
-        num = hadi.make_numerics(m1, m2, 0.8, style, put, scheme, divs, boundary=bc, dividend_schedule=div_all)
+        num = hadi.make_numerics(m1, m2, theta, style, put, scheme, divs, boundary=bc, dividend_schedule=div_all)
         Ns = [N + int(x) for x in rng.integers(0, 4, nopt)] if big else [N] * nopt
         pts, n = hadi.make_points(Ks, T, Ns)
         g = ctx.price_batch(mdl, num, pts, n, want_U=not big, want_lambda=bool(style) and not big)
@@ -50,11 +54,12 @@ while time.time() - t0 < budget:
         continue
     cases += 1
     kinds["big batches"] = kinds.get("big batches", 0) + int(big)
-    info = "m1=%d m2=%d scheme=%d style=%d put=%d bc=%d nd=%d all=%d N=%d n=%d" % (m1, m2, scheme, style, put, bc, nd, div_all, N, nopt)
+    info = "m1=%d m2=%d scheme=%d style=%d put=%d bc=%d nd=%d all=%d N=%d n=%d theta=%g S0=%g r_d=%g V0=%g" % (
+        m1, m2, scheme, style, put, bc, nd, div_all, N, nopt, theta, base["S0"], base["r_d"], base["V0"])
     for k, K in enumerate(Ks):
         if big and k % 37 != 0:
             continue
-        o = O.solve(K, Ns[k], T / Ns[k], m1=m1, m2=m2, theta=0.8, style=style, divs=divs, payoff_put=put, scheme=scheme, bc=bc,
+        o = O.solve(K, Ns[k], T / Ns[k], m1=m1, m2=m2, theta=theta, style=style, divs=divs, payoff_put=put, scheme=scheme, bc=bc,
                     div_all=div_all, want_lambda=bool(style), **base)
         ok = g["prices"][k] == o["price"] and (big or np.array_equal(g["U"][k], o["U"], equal_nan=True))
         if style and not big:
