@@ -648,10 +648,12 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
     plan = plan_hit->second.second;
   } else {
     const bool cs = num->scheme != HADI_DOUGLAS;   // the Craig-Sneyd family runs on the global-state kernels
-    // few large solves: spread each over a thread-block cluster (needs the global working set; the dividend
-    // jump keeps per-CTA tables and stays on the one-CTA-per-solve kernels)
+    // Few large solves run on the wide kernel (below).  The thread-block-cluster kernel of round 1 is no longer a
+    // planner choice — only HADI_FORCE_VARIANT=7 reaches it (hadi_douglas_plan honours the forced id itself); where the
+    // wide kernel does not take a grid, few solves run one CTA per solve like many.
     const int n_it = (item_end < 0 ? n * n_columns(mode) : item_end) - item_begin;
-    const bool few = n_it * HADI_CLUSTER <= 148 && num->num_dividends == 0;
+    (void)n_it;
+    const bool few = false;
     int prc = hadi_douglas_plan(ctx->device, m1, m2, g.ld, g.n1, g.n2, g.pj, cs, &plan, few, many_items);
     // grids beyond shared memory run on the global-state kernel (working set in L2-resident scratch)
     if (prc < 0 && !cs) prc = hadi_douglas_plan(ctx->device, m1, m2, g.ld, g.n1, g.n2, g.pj, true, &plan, few);

@@ -44,6 +44,8 @@ while time.time() - t0 < budget:
         nopt = int(rng.integers(300, 1100))
     Ks = [float(k) for k in rng.uniform(80.0, 120.0, nopt)]
     mdl = hadi.make_model(**base)
+    if os.environ.get("FUZZ_VERBOSE"):
+        print("start m1=%d m2=%d scheme=%d style=%d put=%d bc=%d nd=%d all=%d N=%d n=%d" % (m1, m2, scheme, style, put, bc, nd, div_all, N, nopt), flush=True)
     try:
         num = hadi.make_numerics(m1, m2, theta, style, put, scheme, divs, boundary=bc, dividend_schedule=div_all)
         Ns = [N + int(x) for x in rng.integers(0, 4, nopt)] if big else [N] * nopt
@@ -53,6 +55,8 @@ while time.time() - t0 < budget:
         kinds["refused: " + str(e)[:60]] = kinds.get("refused: " + str(e)[:60], 0) + 1
         continue
     cases += 1
+    if os.environ.get("FUZZ_VERBOSE"):
+        print("case", cases, "m1=%d m2=%d scheme=%d style=%d nd=%d N=%d n=%d" % (m1, m2, scheme, style, nd, N, nopt), "%.2fs" % (time.time() - t0), flush=True)
     kinds["big batches"] = kinds.get("big batches", 0) + int(big)
     info = "m1=%d m2=%d scheme=%d style=%d put=%d bc=%d nd=%d all=%d N=%d n=%d theta=%g S0=%g r_d=%g V0=%g" % (
         m1, m2, scheme, style, put, bc, nd, div_all, N, nopt, theta, base["S0"], base["r_d"], base["V0"])
