@@ -5,6 +5,7 @@ indices.  The implementation is bit-faithful, so the tests demand EQUALITY of ev
 zeros aside) — which also makes the Jacobian, a 1e-6 forward difference, exact.
 """
 import hashlib
+import os
 import math
 
 import numpy as np
@@ -970,3 +971,20 @@ def test_convergence_study_harness(hadi, ctx, oracle, tmp_path):
     lines = open(path).read().splitlines()
     assert lines[0] == "m1,m2,price,error,time" and len(lines) == 1 + len(sizes)
     assert lines[1] == "30,15,%.10e,%.10e,%.10e" % (p[0], e[0], t[0])
+
+
+def test_randomised_differential_against_the_restatement():
+    """A few seconds of tools/fuzz_vs_oracle.py and tools/fuzz_jacobian.py (fixed seeds): random grid shapes from 6x4 up,
+    styles, payoffs, dividend sets, schemes, boundary sets, rates, theta, step counts, batches beyond the persistent grid;
+    random multi-maturity Jacobians and short LM runs on both solver-call schedules.  The long runs behind DESIGN.md section
+    7 found two scratch overruns on small grids; this keeps a sample of them in the suite."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for tool, secs, seed in (("fuzz_vs_oracle.py", "6", "101"), ("fuzz_jacobian.py", "5", "102")):
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", tool), secs, seed], capture_output=True, text=True,
+                           timeout=240)
+        assert r.returncode == 0, r.stderr[-2000:]
+        last = r.stdout.strip().splitlines()[-1]
+        assert "mismatches 0" in last, r.stdout[-2000:]
