@@ -544,8 +544,13 @@ __global__ void __launch_bounds__(kWideThreads, 1) hadi_wide_kernel(const HadiLa
   // the row buffers of a resident team member hold its factors for the whole solve: the column buffers then sit behind them
   if (g.resident) {
     const int used = 6 * g.RB * g.pr;
-    g.CB = min(max_col, (line_doubles - used) / (3 * g.pc));
-    g.cb = lines + used;
+    const int cb_behind = (line_doubles - used) / (3 * g.pc);
+    if (cb_behind >= 1) {
+      g.CB = min(max_col, cb_behind);
+      g.cb = lines + used;
+    } else {
+      g.resident = false;   // no room left for even one column: the factors are reloaded per batch, the arena is shared
+    }
   }
   g.cd = g.cb + (size_t)g.CB * g.pc;
   g.cl = g.cd + (size_t)g.CB * g.pc;

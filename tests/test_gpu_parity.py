@@ -459,6 +459,25 @@ def test_tiny_grids_match_oracle(hadi, ctx, oracle, m1, m2):
     assert np.array_equal(J, Jo) and np.array_equal(b, bo)
 
 
+@pytest.mark.timeout(120)
+def test_wide_kernel_when_resident_rows_fill_the_arena(hadi, ctx, oracle):
+    """257 x 201 nodes, 8 solves: teams of 18 CTAs, twelve rows per CTA whose operand streams fill the shared-memory arena
+    to the last column buffer.  The first version of the kernel computed a column batch of ZERO there and never left the
+    column stage (found by tools/fuzz_vs_oracle.py as a hang); the rows now give up residency when no column fits."""
+    m1, m2, N = 256, 200, 2
+    mdl = hadi.make_model(**BASE)
+    num = hadi.make_numerics(m1, m2, 0.8, hadi.EUROPEAN, hadi.CALL, hadi.CRAIG_SNEYD, None)
+    Ks = [96.0 + k for k in range(8)]
+    pts, n = hadi.make_points(Ks, 0.02, N)
+    bt = ctx.batch(mdl, num, pts, n)
+    assert bt.kernel_info == (9, 144, 18)
+    bt.destroy()
+    g = ctx.price_batch(mdl, num, pts, n, want_U=True)
+    for k in (0, 7):
+        o = oracle.solve(Ks[k], N, 0.01, m1=m1, m2=m2, theta=0.8, scheme=1, want_lambda=False, **BASE)
+        assert g["prices"][k] == o["price"] and np.array_equal(g["U"][k], o["U"])
+
+
 def test_config4_full_size_golden(hadi, ctx):
     """BASELINE config 4 at full size: European call, 400 x 200 x 200.  Golden prices from the reference's
     own code (SURVEY.md 8(c) probe): Craig-Sneyd host solver and device Douglas path."""
