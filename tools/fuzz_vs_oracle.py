@@ -38,6 +38,8 @@ while time.time() - t0 < budget:
                 rho=float(rng.uniform(-0.9, 0.3)), sigma=float(rng.uniform(0.1, 0.6)), kappa=float(rng.uniform(0.5, 3.0)),
                 eta=float(rng.uniform(0.02, 0.1)))
     nopt = int(rng.choice([1, 2, 5]))
+    if os.environ.get("FUZZ_LARGE") and rng.uniform() < 0.3:
+        nopt = int(rng.choice([9, 17, 33, 45]))   # teams of 16, 8, 4 CTAs (rows not resident) and the one-CTA kernel
     big = scheme == 0 and rng.uniform() < 0.03   # now and then a batch beyond the persistent grid (split schedule, variant 11)
     if big:
         m1, m2 = [(50, 25), (100, 50), (40, 20)][int(rng.integers(0, 3))]
@@ -61,7 +63,7 @@ while time.time() - t0 < budget:
     info = "m1=%d m2=%d scheme=%d style=%d put=%d bc=%d nd=%d all=%d N=%d n=%d theta=%g S0=%g r_d=%g V0=%g" % (
         m1, m2, scheme, style, put, bc, nd, div_all, N, nopt, theta, base["S0"], base["r_d"], base["V0"])
     for k, K in enumerate(Ks):
-        if big and k % 37 != 0:
+        if (big and k % 37 != 0) or (not big and nopt > 5 and k % 8 != 0):
             continue
         o = O.solve(K, Ns[k], T / Ns[k], m1=m1, m2=m2, theta=theta, style=style, divs=divs, payoff_put=put, scheme=scheme, bc=bc,
                     div_all=div_all, want_lambda=bool(style), **base)
