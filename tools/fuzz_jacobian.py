@@ -25,6 +25,10 @@ while time.time() - t0 < budget:
                 rho=float(rng.uniform(-0.9, 0.3)), sigma=float(rng.uniform(0.1, 0.6)), kappa=float(rng.uniform(0.5, 3.0)),
                 eta=float(rng.uniform(0.02, 0.1)))
     nopt = int(rng.integers(1, 9))
+    if rng.uniform() < 0.04:   # a Jacobian batch that fills the small-CTA instantiation of the 51 x 26 grid (>= 888 items)
+        m1, m2, nopt = 50, 25, int(rng.integers(150, 260))
+    elif rng.uniform() < 0.04:   # and one beyond the persistent grid at 101 x 51 (split schedule)
+        m1, m2, nopt = 100, 50, int(rng.integers(60, 140))
     Ks = [float(k) for k in rng.uniform(85.0, 115.0, nopt)]
     Ts = [float(t) for t in rng.choice([0.5, 1.0, 1.5], nopt)]
     Ns = [int(x) for x in rng.integers(2, 9, nopt)]
