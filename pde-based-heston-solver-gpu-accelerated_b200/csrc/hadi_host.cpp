@@ -640,6 +640,7 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
                                             std::string(getenv("HADI_NO_DUO") ? getenv("HADI_NO_DUO") : ""));
   const auto plan_hit = ctx->plans.find(plan_key);
   const bool forced_wide = forced_variant && atoi(forced_variant) == HADI_WIDE_VARIANT;
+  bool no_base_plan = false;
   if (forced_variant && atoi(forced_variant) == 7 && num->num_dividends > 0)   // the planner never pairs them; a forced run must not skip the jumps silently
     return fail(ctx, HADI_ERR_ARG, "the cluster kernel (variant 7) does not take dividend jumps");
   if (forced_wide) {
@@ -663,9 +664,9 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
       if (hadi_douglas_plan(ctx->device, m1, m2, g.ld, g.n1, g.n2, g.pj, true, &cplan, true) == 0 && cplan.cluster > 1)
         plan = cplan;
     }
-    if (prc < 0) return fail(ctx, HADI_ERR_SMEM, "grid too large: m1+1 <= 1024 and the coefficient tables must fit shared memory");
     if (prc > 0) return cuda_fail(ctx, (cudaError_t)prc, "kernel plan");
-    ctx->plans[plan_key] = std::make_pair(0, plan);
+    if (prc < 0) no_base_plan = true;   // no one-CTA kernel takes this grid: the wide kernel may (it needs m2 + 1 <= 511 only)
+    else ctx->plans[plan_key] = std::make_pair(0, plan);
   }
   // A few solves that need the global working set (large grids, the Craig-Sneyd family): the
   // wide kernel spreads each over a team of co-resident CTAs (hadi_wide.cu).  HADI_WIDE_MAX_ITEMS moves the threshold
@@ -678,7 +679,8 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
     // Grids so small that the A2 assembly scratch (TS_COUNT rows of n2 doubles) does not fit the Y array the other
     // kernels borrow for it (roughly m1 < 20) also go to the wide kernel, whatever the batch: it has its own arena.
     const bool tiny_grid = (size_t)TS_COUNT * g.n2 > (size_t)(m2 + 1) * g.ld;
-    if (n_it_plan >= 1 && (forced_wide || tiny_grid || (!forced_variant && plan.global_state && n_it_plan <= wide_max))) {
+    if (n_it_plan >= 1 && (forced_wide || tiny_grid || (no_base_plan && !forced_variant) ||
+                           (!forced_variant && !no_base_plan && plan.global_state && n_it_plan <= wide_max))) {
       const auto wkey = std::make_tuple(num->m1, num->m2, num->scheme, 2, std::string("wide"));
       auto wh = ctx->plans.find(wkey);
       if (wh == ctx->plans.end()) {
@@ -689,10 +691,13 @@ int hadi_batch_create_ex(hadi_ctx* ctx, const hadi_model* model, const hadi_nume
       if (wh->second.first == 0) {
         plan = wh->second.second;
         plan.cluster = hadi_wide_team(n_it_plan, plan.sm_count, m1, m2);
-      } else if (forced_wide || tiny_grid) {
-        return fail(ctx, HADI_ERR_SMEM, "the wide kernel does not take this grid");
+      } else if (forced_wide || tiny_grid || no_base_plan) {
+        return fail(ctx, HADI_ERR_SMEM, no_base_plan ? "grid too large: m1+1 <= 1024, m2+1 <= 511 and the coefficient tables must fit shared memory"
+                                                     : "the wide kernel does not take this grid");
       }
+      no_base_plan = false;
     }
+    if (no_base_plan) return fail(ctx, HADI_ERR_SMEM, "grid too large: m1+1 <= 1024 and the coefficient tables must fit shared memory");
   }
 
   std::unique_ptr<hadi_batch> b(new hadi_batch());

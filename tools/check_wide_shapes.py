@@ -10,7 +10,7 @@ divs = ([0.2, 0.4, 0.6, 0.8], [0.5, 0.3, 0.2, 0.1], [0.02] * 4)
 ctx = hadi.Context(0)
 mdl = hadi.make_model(**BASE)
 bad = 0
-for (m1, m2) in ((8, 4), (12, 12), (37, 36), (63, 31), (64, 32), (129, 65), (255, 127), (256, 128), (511, 255), (600, 100), (1000, 60)):
+for (m1, m2) in ((8, 4), (12, 12), (37, 36), (63, 31), (64, 32), (129, 65), (255, 127), (256, 128), (511, 255), (600, 100), (1000, 60), (600, 510), (760, 400), (1023, 200), (300, 299)):
     for scheme, style, dv in ((0, 1, divs), (1, 0, None), (3, 0, None)):
         for nopt in (1, 3, 11):
             num = hadi.make_numerics(m1, m2, 0.8, style, hadi.CALL, scheme, dv)
